@@ -1,0 +1,123 @@
+/* mcrg_b200 — C ABI of the B200-native MCRG hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no CUDA or torch types.  Each entry point names the
+ * reference interface it replaces (file:line under the reference's src/).  The reference has no device code and
+ * no FFI of its own; the binding a maintainer would add is the set of C++ classes in mcrg_b200/host/ (same class
+ * names and signatures as lattice.hpp / ising.hpp / mcrg.hpp), shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative mcrg_status on failure; mcrg_last_error() describes the
+ *     last failure of the calling thread.  The reference has no error handling at all.
+ *   - one context = one device = a batch of `n_replicas` independent L x L periodic Ising lattices (the
+ *     reference runs one chain per MPI rank: mcrg.cpp:42-50); a context is not thread-safe, distinct contexts
+ *     may be used from distinct threads.
+ *   - spins cross the boundary in the reference's layout: int32 +-1, column-major, element (i,j) at j*L+i
+ *     (definitions.hpp:16), replicas concatenated.
+ *   - L must be a power of two, 4 <= L <= 16384.
+ *   - all work is enqueued on the context's stream; calls that return host data synchronise it.
+ *   - the library is CUDA-only: if no device is present every call fails with MCRG_ERR_CUDA.  There is no CPU
+ *     path in the product.
+ */
+#ifndef MCRG_B200_H
+#define MCRG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcrg_ctx mcrg_ctx;
+
+enum mcrg_status {
+    MCRG_OK = 0,
+    MCRG_ERR_ARG = -1,   /* bad argument (size not a power of two, index out of range, ...) */
+    MCRG_ERR_CUDA = -2,  /* a CUDA runtime call failed (including "no device") */
+    MCRG_ERR_STATE = -3  /* call not valid in the current state */
+};
+
+/* operators measured at every blocking level, in this order */
+enum { MCRG_OP_NN = 0, MCRG_OP_NNN = 1, MCRG_OP_PLAQ = 2, MCRG_OP_SUM = 3, MCRG_NOBS = 4 };
+#define MCRG_MAX_LEVELS 15
+#define MCRG_NOP 3 /* even operators entering the RG matrix: NN, NNN, PLAQ (the reference uses the first two) */
+
+const char *mcrg_last_error(void);
+int mcrg_device_count(int *n);
+int mcrg_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* Replaces `new Lattice(N)` per rank (lattice.cpp:3-15, mcrg.cpp:49).  replica_base = global id of replica 0
+ * (enters every Philox counter, so results do not depend on how replicas are spread over devices).
+ * n_bins >= 1 accumulator bins per replica.  The lattices start all-up; call mcrg_init_hot for the reference's
+ * hot start. */
+int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t replica_base, int n_bins,
+                    mcrg_ctx **out);
+int mcrg_ctx_destroy(mcrg_ctx *ctx);
+int mcrg_sync(mcrg_ctx *ctx);
+/* the cudaStream_t the context enqueues on, as an integer handle (for event timing by the caller) */
+uint64_t mcrg_stream_handle(mcrg_ctx *ctx);
+/* device-side timing on the context's stream */
+int mcrg_timer_start(mcrg_ctx *ctx);
+int mcrg_timer_stop(mcrg_ctx *ctx, float *ms);
+int mcrg_levels_full(int L); /* floor(log L / log 2) - 1, mcrg.cpp:43 */
+/* tuning knobs: rows per strip of the sweep kernel (0 = heuristic), sweeps fused per launch, CUDA-graph use */
+int mcrg_set_tuning(mcrg_ctx *ctx, int strip_rows, int fuse_sweeps, int use_graphs);
+
+/* ---- state ---------------------------------------------------------------------------------------------- */
+/* IsingModel(K) (ising.cpp:3-11): n = 1 (all replicas) or n = n_replicas.  K < 0 is ferromagnetic. */
+int mcrg_set_couplings(mcrg_ctx *ctx, const double *K, int n);
+/* Lattice::initialize_random_spins (lattice.cpp:33-41): i.i.d. fair spins, here from Philox(seed, replica) */
+int mcrg_init_hot(mcrg_ctx *ctx);
+int mcrg_init_cold(mcrg_ctx *ctx);
+/* Lattice(int a, imat spins) (lattice.cpp:18-30) / reading Lattice::spins_ (lattice.hpp:16) */
+int mcrg_set_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, const int32_t *host_spins);
+int mcrg_get_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, int32_t *host_spins);
+/* block spins produced by the last measurement; level in 1..levels of that measurement; (L>>level)^2 ints */
+int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *ctx, int replica, int level, int32_t *host_spins);
+int mcrg_get_sweep_counter(mcrg_ctx *ctx, uint64_t *t);
+int mcrg_set_sweep_counter(mcrg_ctx *ctx, uint64_t t);
+
+/* ---- the hot path --------------------------------------------------------------------------------------- */
+/* IsingModel::sample_new_configuration x n (ising.cpp:87-93) and IsingModel::equilibrate(.., n, false)
+ * (ising.cpp:14-84): n full checkerboard Metropolis sweeps of every replica. */
+int mcrg_sweep(mcrg_ctx *ctx, int n_sweeps);
+/* Lattice::calc_interactions at every blocking level of the current configurations (lattice.cpp:102-120 after
+ * repeated block_spin_transformation, mcrg.cpp:314-348; ties by Philox keyed with the sweep counter).
+ * max_levels < 0: full pyramid.  S (optional) receives [replica][n_lv+1][MCRG_NOBS]; *n_lv_out the level count. */
+int mcrg_measure(mcrg_ctx *ctx, int max_levels, int64_t *S, int *n_lv_out);
+/* level-0 sums per replica: calc_interactions, calc_nearest_neighbor_interaction (lattice.cpp:84-120), the
+ * spin sum behind calc_magnetization (ising.cpp:176-179) and the plaquette sum.  Any pointer may be NULL. */
+int mcrg_observables(mcrg_ctx *ctx, int64_t *Snn, int64_t *Snnn, int64_t *Splaq, int64_t *M);
+/* the sample loop of calc_critical_exponent (mcrg.cpp:72-98), n_samples times for every replica:
+ *   measure the current configuration at all levels, add S, S(n) x S(n-1), S(n) x S(n) into bin `bin`,
+ *   then sweeps_per_sample Metropolis sweeps. */
+int mcrg_run(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, int max_levels, int bin);
+
+/* Measurement aid: runs n_samples samples of mcrg_run (bin 0) with an event between the kernels and returns the
+ * average device time in ms per sample of {measure+first-sweep kernel, further sweep kernels, level kernels,
+ * tail kernel}.  The chain and the accumulators advance exactly as in mcrg_run. */
+int mcrg_profile_kernels(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, int max_levels, float out_ms[4]);
+
+/* ---- accumulators (mcrg.cpp:53-70 containers), exact 128-bit integers ------------------------------------ */
+typedef struct {
+    int n_slots, n_dslots;
+    int slot_n, slot_absm, slot_m2; /* samples, sum |M|, sum M^2 */
+    int slot_s;   /* + lv*MCRG_NOP + op                sum S^(lv)_op                         */
+    int slot_ss;  /* + lv*9 + b*MCRG_NOP + a           sum S^(lv)_a S^(lv)_b   (Sb_Sb of level lv, mcrg.cpp:89) */
+    int slot_sbs; /* + (n-1)*9 + b*MCRG_NOP + a        sum S^(n)_a S^(n-1)_b   (Sb_S, mcrg.cpp:88), flatten order
+                                                       of definitions.cpp:9-19 */
+    int dslot_m4; /* sum M^4 (double) */
+} mcrg_acc_layout;
+int mcrg_accumulators_layout(mcrg_acc_layout *out);
+int mcrg_accumulators_reset(mcrg_ctx *ctx);
+/* hi/lo: [replica][bin][n_slots]; d: [replica][bin][n_dslots]; any may be NULL */
+int mcrg_accumulators_get(mcrg_ctx *ctx, int64_t *hi, uint64_t *lo, double *d);
+/* totals over this context's replicas and bins as 32-bit limbs held in int64 (4 limbs per slot, little endian,
+ * top limb signed): summing such vectors over ranks with an int64 all-reduce (NCCL ncclInt64/ncclSum) is exact
+ * and order independent for up to 2^31 ranks — the collective of mcrg.cpp:101-103.  The vector is written to
+ * DEVICE memory `dev_out` (4*n_slots int64) on the context's stream; pass it straight to the all-reduce. */
+int mcrg_accumulators_total_limbs_device(mcrg_ctx *ctx, void *dev_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,227 @@
+"""ctypes binding of include/mcrg_b200.h.  Thin: every method is one C call; no compute happens here.
+
+There is no CPU path: if libmcrg_b200.so is missing, or no CUDA device is present, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcrg_b200.so")
+
+MAX_LEVELS = 15
+NOP = 3
+NOBS = 4
+
+
+class McrgError(RuntimeError):
+    pass
+
+
+class AccLayout(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_slots", "n_dslots", "slot_n", "slot_absm", "slot_m2", "slot_s", "slot_ss",
+                                       "slot_sbs", "dslot_m4")]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library (never builds it, never falls back)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise McrgError(f"{LIB_PATH} is missing: run `python -m mcrg_b200.build` (nvcc, sm_100a); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        P = C.POINTER
+        vp = C.c_void_p
+        l.mcrg_last_error.restype = C.c_char_p
+        l.mcrg_device_count.argtypes = [P(C.c_int)]
+        l.mcrg_version.restype = C.c_int
+        l.mcrg_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_int, P(vp)]
+        l.mcrg_ctx_destroy.argtypes = [vp]
+        l.mcrg_sync.argtypes = [vp]
+        l.mcrg_stream_handle.argtypes = [vp]
+        l.mcrg_stream_handle.restype = C.c_uint64
+        l.mcrg_timer_start.argtypes = [vp]
+        l.mcrg_timer_stop.argtypes = [vp, P(C.c_float)]
+        l.mcrg_levels_full.argtypes = [C.c_int]
+        l.mcrg_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        l.mcrg_set_couplings.argtypes = [vp, vp, C.c_int]
+        l.mcrg_init_hot.argtypes = [vp]
+        l.mcrg_init_cold.argtypes = [vp]
+        l.mcrg_set_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
+        l.mcrg_get_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
+        l.mcrg_get_level_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
+        l.mcrg_get_sweep_counter.argtypes = [vp, P(C.c_uint64)]
+        l.mcrg_set_sweep_counter.argtypes = [vp, C.c_uint64]
+        l.mcrg_sweep.argtypes = [vp, C.c_int]
+        l.mcrg_measure.argtypes = [vp, C.c_int, vp, P(C.c_int)]
+        l.mcrg_observables.argtypes = [vp, vp, vp, vp, vp]
+        l.mcrg_run.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.mcrg_profile_kernels.argtypes = [vp, C.c_int, C.c_int, C.c_int, P(C.c_float)]
+        l.mcrg_accumulators_layout.argtypes = [P(AccLayout)]
+        l.mcrg_accumulators_reset.argtypes = [vp]
+        l.mcrg_accumulators_get.argtypes = [vp, vp, vp, vp]
+        l.mcrg_accumulators_total_limbs_device.argtypes = [vp, vp]
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise McrgError(f"mcrg_b200 error {rc}: {lib().mcrg_last_error().decode()}")
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().mcrg_device_count(C.byref(n)))
+    return n.value
+
+
+def acc_layout():
+    lay = AccLayout()
+    _check(lib().mcrg_accumulators_layout(C.byref(lay)))
+    return lay
+
+
+def levels_full(L):
+    return lib().mcrg_levels_full(L)
+
+
+class Context:
+    """A batch of `n_replicas` L x L lattices on one device (mcrg_ctx)."""
+
+    def __init__(self, L, n_replicas, seed=12345, device=0, replica_base=0, n_bins=1):
+        self._h = C.c_void_p()
+        self.L, self.n_replicas, self.n_bins, self.device = L, n_replicas, n_bins, device
+        rc = lib().mcrg_ctx_create(device, L, n_replicas, seed, replica_base, n_bins, C.byref(self._h))
+        if rc != 0:
+            msg = lib().mcrg_last_error().decode()
+            if self._h:
+                lib().mcrg_ctx_destroy(self._h)
+                self._h = C.c_void_p()
+            raise McrgError(f"mcrg_ctx_create failed ({rc}): {msg}")
+
+    def close(self):
+        if self._h:
+            lib().mcrg_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- state
+    def sync(self):
+        _check(lib().mcrg_sync(self._h))
+
+    @property
+    def stream_handle(self):
+        return lib().mcrg_stream_handle(self._h)
+
+    def timer_start(self):
+        _check(lib().mcrg_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(lib().mcrg_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def set_tuning(self, strip_rows=0, fuse_sweeps=1, use_graphs=1):
+        _check(lib().mcrg_set_tuning(self._h, strip_rows, fuse_sweeps, use_graphs))
+
+    def set_couplings(self, K):
+        K = np.ascontiguousarray(np.atleast_1d(np.asarray(K, np.float64)))
+        _check(lib().mcrg_set_couplings(self._h, K.ctypes.data, K.size))
+
+    def init_hot(self):
+        _check(lib().mcrg_init_hot(self._h))
+
+    def init_cold(self):
+        _check(lib().mcrg_init_cold(self._h))
+
+    def set_spins(self, spins, first=0):
+        """spins: [count, L, L] int32 in the reference layout (arr[r, j, i])."""
+        spins = np.ascontiguousarray(spins, np.int32).reshape(-1, self.L, self.L)
+        _check(lib().mcrg_set_spins_i32_colmajor(self._h, first, spins.shape[0], spins.ctypes.data))
+
+    def set_spins_ptr(self, host_ptr, count, first=0):
+        """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        _check(lib().mcrg_set_spins_i32_colmajor(self._h, first, count, C.c_void_p(host_ptr)))
+
+    def get_spins(self, first=0, count=None):
+        count = self.n_replicas - first if count is None else count
+        out = np.empty((count, self.L, self.L), np.int32)
+        _check(lib().mcrg_get_spins_i32_colmajor(self._h, first, count, out.ctypes.data))
+        return out
+
+    def get_level_spins(self, replica, level):
+        n = self.L >> level
+        out = np.empty((n, n), np.int32)
+        _check(lib().mcrg_get_level_spins_i32_colmajor(self._h, replica, level, out.ctypes.data))
+        return out
+
+    @property
+    def sweep_counter(self):
+        t = C.c_uint64(0)
+        _check(lib().mcrg_get_sweep_counter(self._h, C.byref(t)))
+        return t.value
+
+    @sweep_counter.setter
+    def sweep_counter(self, t):
+        _check(lib().mcrg_set_sweep_counter(self._h, t))
+
+    # ---- hot path
+    def sweep(self, n):
+        _check(lib().mcrg_sweep(self._h, n))
+
+    def measure(self, max_levels=-1):
+        """-> S[replica, level, {nn, nnn, plaq, sum}] of the current configurations."""
+        n_lv = min(levels_full(self.L), max_levels) if max_levels >= 0 else levels_full(self.L)
+        S = np.zeros((self.n_replicas, n_lv + 1, NOBS), np.int64)
+        got = C.c_int(0)
+        _check(lib().mcrg_measure(self._h, max_levels, S.ctypes.data, C.byref(got)))
+        assert got.value == n_lv
+        return S
+
+    def observables(self):
+        out = [np.zeros(self.n_replicas, np.int64) for _ in range(4)]
+        _check(lib().mcrg_observables(self._h, *[o.ctypes.data for o in out]))
+        return dict(Snn=out[0], Snnn=out[1], Splaq=out[2], M=out[3])
+
+    def run(self, n_samples, sweeps_per_sample=1, max_levels=-1, bin=0):
+        _check(lib().mcrg_run(self._h, n_samples, sweeps_per_sample, max_levels, bin))
+
+    def profile_kernels(self, n_samples, sweeps_per_sample=1, max_levels=-1):
+        """-> dict of average device ms per sample for each kernel class (events between the launches)."""
+        out = (C.c_float * 4)()
+        _check(lib().mcrg_profile_kernels(self._h, n_samples, sweeps_per_sample, max_levels, out))
+        return dict(sweep_measure=out[0], sweep_only=out[1], level=out[2], tail=out[3])
+
+    # ---- accumulators
+    def reset_accumulators(self):
+        _check(lib().mcrg_accumulators_reset(self._h))
+
+    def accumulators(self):
+        """-> (acc, accd): acc is an object array [replica, bin, slot] of exact Python ints, accd float64."""
+        lay = acc_layout()
+        shape = (self.n_replicas, self.n_bins, lay.n_slots)
+        hi = np.zeros(shape, np.int64)
+        lo = np.zeros(shape, np.uint64)
+        d = np.zeros((self.n_replicas, self.n_bins, lay.n_dslots), np.float64)
+        _check(lib().mcrg_accumulators_get(self._h, hi.ctypes.data, lo.ctypes.data, d.ctypes.data))
+        acc = hi.astype(object) * (1 << 64) + lo.astype(object)
+        return acc, d
+
+    def total_limbs_to_device(self, dev_ptr):
+        _check(lib().mcrg_accumulators_total_limbs_device(self._h, C.c_void_p(dev_ptr)))

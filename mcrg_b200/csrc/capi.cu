@@ -1,0 +1,653 @@
+// extern "C" layer of libmcrg_b200.so (include/mcrg_b200.h): context management and launch sequencing.
+// No compute happens on the host; every function either enqueues kernels from kernels.cu or moves bytes.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mcrg_b200.h"
+#include "kernels.cuh"
+
+using namespace mcrg;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(MCRG_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2h(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) ++l;
+    return l;
+}
+
+struct GraphKey {
+    int m, n_lv, bin, chunk, cur, R, fuse;
+    bool operator<(const GraphKey &o) const {
+        return std::tie(m, n_lv, bin, chunk, cur, R, fuse) < std::tie(o.m, o.n_lv, o.bin, o.chunk, o.cur, o.R, o.fuse);
+    }
+};
+
+}  // namespace
+
+struct mcrg_ctx {
+    int device = 0, L = 0, W = 0, bits = 0, n_replicas = 0, n_bins = 1, full_levels = 0;
+    uint64_t seed = 0;
+    uint32_t replica_base = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t *planes[2] = {nullptr, nullptr};
+    int cur = 0;
+    uint32_t *levels = nullptr;
+    size_t level_off[MAX_LEVELS + 1] = {0};
+    size_t *d_level_off = nullptr;
+    unsigned long long *cnt = nullptr;
+    long long *S_out = nullptr;
+    unsigned long long *acc_lo = nullptr;
+    long long *acc_hi = nullptr;
+    double *acc_d = nullptr;
+    uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr;
+    unsigned long long *d_t = nullptr;
+    unsigned long long t_host = 0;
+    int32_t *stage = nullptr;
+    size_t stage_ints = 0;
+    int last_levels = 0;
+    int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+};
+
+namespace {
+
+int choose_R(const mcrg_ctx *c, int H) {
+    const int L = c->L, W = c->W;
+    const int max_smem = sweep0_max_smem();
+    auto fits = [&](int R) { return (long long)sweep0_smem_bytes(L, R, H) <= (long long)max_smem - 1024; };
+    if (c->strip_rows >= 2 && c->strip_rows <= L && is_pow2(c->strip_rows) && fits(c->strip_rows)) return c->strip_rows;
+    int R = 4096 / W;
+    if (R > 64) R = 64;
+    if (R < 16) R = 16;
+    if (R > L) R = L;
+    while (R > 2 && !fits(R)) R >>= 1;
+    // keep every SM busy: at least two CTAs per SM when the batch is small
+    while (R > 8 && (long long)c->n_replicas * (L / R) < 2 * 148) R >>= 1;
+    return R;
+}
+
+int choose_Rn(int Ln) {
+    const int Wn = nat_words(Ln);
+    int R = 4096 / Wn;
+    if (R > 64) R = 64;
+    if (R < 2) R = 2;
+    if (R > Ln) R = Ln;
+    return R;
+}
+
+int ensure_stage(mcrg_ctx *c, size_t ints) {
+    if (c->stage_ints >= ints) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr;
+    c->stage_ints = 0;
+    CK(cudaMalloc(&c->stage, ints * sizeof(int32_t)));
+    c->stage_ints = ints;
+    return 0;
+}
+
+SweepArgs sweep_args(const mcrg_ctx *c, int R, int nsw, unsigned long long t_off) {
+    SweepArgs a;
+    a.src = c->planes[c->cur];
+    a.dst = c->planes[1 - c->cur];
+    a.level1 = c->levels + c->level_off[1];
+    a.cnt = c->cnt;
+    a.T4 = c->T4;
+    a.T8 = c->T8;
+    a.anti = c->anti;
+    a.d_t = c->d_t;
+    a.t_off = t_off;
+    a.seed = c->seed;
+    a.replica_base = c->replica_base;
+    a.L = c->L;
+    a.W = c->W;
+    a.bits = c->bits;
+    a.R = R;
+    a.H = nsw > 0 ? 2 * nsw : 2;
+    a.nsw = nsw;
+    a.strips = c->L / R;
+    return a;
+}
+
+// enqueue nsw sweeps (no measurement), fused `fuse` per launch; flips c->cur per launch
+void enqueue_sweeps(mcrg_ctx *c, int n, unsigned long long t_off) {
+    int done = 0;
+    while (done < n) {
+        const int k = (n - done) < c->fuse_sweeps ? (n - done) : c->fuse_sweeps;
+        const int R = choose_R(c, 2 * k);
+        SweepArgs a = sweep_args(c, R, k, t_off + done);
+        launch_sweep0(a, c->n_replicas, false, c->stream);
+        c->cur ^= 1;
+        done += k;
+    }
+}
+
+// enqueue: measure the current configuration at levels 0..n_lv (+ accumulate), fused with the first of
+// `m` sweeps; then the remaining m-1 sweeps.
+void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsigned long long t_off,
+                    cudaEvent_t *probe = nullptr) {
+    const int first = m > 0 ? 1 : 0;
+    const int R = choose_R(c, 2);
+    SweepArgs a = sweep_args(c, R, first, t_off);
+    if (probe) cudaEventRecord(probe[0], c->stream);
+    launch_sweep0(a, c->n_replicas, true, c->stream);
+    if (probe) cudaEventRecord(probe[1], c->stream);
+    if (first) c->cur ^= 1;
+    int lv = 1;
+    while (lv <= n_lv && (c->L >> lv) > TAIL_MAX_L) {
+        LevelArgs la;
+        la.in = c->levels + c->level_off[lv];
+        la.out = lv < n_lv ? c->levels + c->level_off[lv + 1] : nullptr;
+        la.cnt = c->cnt;
+        la.d_t = c->d_t;
+        la.t_off = t_off;
+        la.seed = c->seed;
+        la.replica_base = c->replica_base;
+        la.Ln = c->L >> lv;
+        la.level = lv;
+        la.R = choose_Rn(la.Ln);
+        la.strips = la.Ln / la.R;
+        launch_level(la, c->n_replicas, c->stream);
+        ++lv;
+    }
+    TailArgs ta;
+    ta.in = lv <= n_lv ? c->levels + c->level_off[lv] : nullptr;
+    ta.levels_out = c->levels;
+    ta.level_off = c->d_level_off;
+    ta.cnt = c->cnt;
+    ta.S_out = c->S_out;
+    ta.acc_lo = c->acc_lo;
+    ta.acc_hi = c->acc_hi;
+    ta.acc_d = c->acc_d;
+    ta.d_t = c->d_t;
+    ta.t_off = t_off;
+    ta.seed = c->seed;
+    ta.replica_base = c->replica_base;
+    ta.L = c->L;
+    ta.start = lv;
+    ta.n_levels = n_lv;
+    ta.n_bins = c->n_bins;
+    ta.bin = bin;
+    ta.accumulate = accumulate;
+    if (probe) cudaEventRecord(probe[2], c->stream);
+    launch_tail(ta, c->n_replicas, c->stream);
+    if (probe) cudaEventRecord(probe[3], c->stream);
+    c->last_levels = n_lv;
+    if (m > 1) enqueue_sweeps(c, m - 1, t_off + 1);
+    if (probe) cudaEventRecord(probe[4], c->stream);
+}
+
+int clamp_levels(const mcrg_ctx *c, int max_levels) {
+    int n_lv = c->full_levels;
+    if (max_levels >= 0 && max_levels < n_lv) n_lv = max_levels;
+    return n_lv;
+}
+
+void destroy_graphs(mcrg_ctx *c) {
+    for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mcrg_last_error(void) { return g_err; }
+
+int mcrg_version(void) { return 100; }
+
+int mcrg_device_count(int *n) {
+    if (!n) return fail(MCRG_ERR_ARG, "null pointer");
+    *n = 0;
+    CK(cudaGetDeviceCount(n));
+    return 0;
+}
+
+int mcrg_levels_full(int L) {
+    if (L < 2) return 0;
+    return (int)std::floor(std::log((double)L) / std::log(2.0) + 1e-9) - 1;  // mcrg.cpp:43
+}
+
+int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t replica_base, int n_bins,
+                    mcrg_ctx **out) {
+    if (!out) return fail(MCRG_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (!is_pow2(L) || L < 4 || L > 16384) return fail(MCRG_ERR_ARG, "L=%d must be a power of two in [4, 16384]", L);
+    if (n_replicas < 1 || n_replicas > 65535) return fail(MCRG_ERR_ARG, "n_replicas=%d out of range [1, 65535]", n_replicas);
+    if (n_bins < 1) return fail(MCRG_ERR_ARG, "n_bins=%d must be >= 1", n_bins);
+    int n_dev = 0;
+    CK(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(MCRG_ERR_CUDA, "device %d not present (%d CUDA devices)", device, n_dev);
+    CK(cudaSetDevice(device));
+    mcrg_ctx *c = new mcrg_ctx();
+    c->device = device;
+    c->L = L;
+    c->W = l0_words(L);
+    c->bits = l0_bits(L);
+    c->n_replicas = n_replicas;
+    c->n_bins = n_bins;
+    c->seed = seed;
+    c->replica_base = replica_base;
+    c->full_levels = ilog2h(L) - 1;
+    if (const char *e = getenv("MCRG_STRIP_ROWS")) c->strip_rows = atoi(e);
+    if (const char *e = getenv("MCRG_FUSE_SWEEPS")) c->fuse_sweeps = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("MCRG_USE_GRAPHS")) c->use_graphs = atoi(e);
+    *out = c;  // so that a failure below can still be cleaned up by mcrg_ctx_destroy
+    sweep0_max_smem();  // opt in to large dynamic shared memory once, outside any stream capture
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    const size_t plane_words = (size_t)n_replicas * 2 * L * c->W;
+    CK(cudaMalloc(&c->planes[0], plane_words * 4));
+    CK(cudaMalloc(&c->planes[1], plane_words * 4));
+    size_t off = 0;
+    for (int lv = 1; lv <= c->full_levels; ++lv) {
+        const int Ln = L >> lv;
+        c->level_off[lv] = off;
+        size_t words = (size_t)n_replicas * Ln * nat_words(Ln);
+        off += (words + 3) & ~(size_t)3;  // keep every level 16-byte aligned for the 128-bit loads
+    }
+    CK(cudaMalloc(&c->levels, (off + 4) * 4));
+    CK(cudaMemsetAsync(c->levels, 0, (off + 4) * 4, c->stream));
+    CK(cudaMalloc(&c->d_level_off, sizeof(c->level_off)));
+    CK(cudaMemcpyAsync(c->d_level_off, c->level_off, sizeof(c->level_off), cudaMemcpyHostToDevice, c->stream));
+    const size_t n_cnt = (size_t)n_replicas * (MAX_LEVELS + 1) * 4;
+    CK(cudaMalloc(&c->cnt, n_cnt * 8));
+    CK(cudaMemsetAsync(c->cnt, 0, n_cnt * 8, c->stream));
+    CK(cudaMalloc(&c->S_out, n_cnt * 8));
+    CK(cudaMemsetAsync(c->S_out, 0, n_cnt * 8, c->stream));
+    const size_t n_acc = (size_t)n_replicas * n_bins * N_SLOTS;
+    CK(cudaMalloc(&c->acc_lo, n_acc * 8));
+    CK(cudaMalloc(&c->acc_hi, n_acc * 8));
+    CK(cudaMalloc(&c->acc_d, (size_t)n_replicas * n_bins * N_DSLOTS * 8));
+    CK(cudaMalloc(&c->T4, n_replicas * 4));
+    CK(cudaMalloc(&c->T8, n_replicas * 4));
+    CK(cudaMalloc(&c->anti, n_replicas * 4));
+    CK(cudaMalloc(&c->d_t, 8));
+    CK(cudaMemsetAsync(c->d_t, 0, 8, c->stream));
+    launch_init_cold(c->planes[0], L, n_replicas, c->stream);
+    CK(cudaGetLastError());
+    int rc = mcrg_accumulators_reset(c);
+    if (rc) return rc;
+    const double Kc = -0.5 * std::log(1.0 + std::sqrt(2.0));  // main.cpp:13
+    rc = mcrg_set_couplings(c, &Kc, 1);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mcrg_ctx_destroy(mcrg_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    destroy_graphs(c);
+    cudaFree(c->planes[0]);
+    cudaFree(c->planes[1]);
+    cudaFree(c->levels);
+    cudaFree(c->d_level_off);
+    cudaFree(c->cnt);
+    cudaFree(c->S_out);
+    cudaFree(c->acc_lo);
+    cudaFree(c->acc_hi);
+    cudaFree(c->acc_d);
+    cudaFree(c->T4);
+    cudaFree(c->T8);
+    cudaFree(c->anti);
+    cudaFree(c->d_t);
+    cudaFree(c->stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int mcrg_sync(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+uint64_t mcrg_stream_handle(mcrg_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+
+int mcrg_timer_start(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+
+int mcrg_timer_stop(mcrg_ctx *c, float *ms) {
+    if (!c || !ms) return fail(MCRG_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+int mcrg_set_tuning(mcrg_ctx *c, int strip_rows, int fuse_sweeps, int use_graphs) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (strip_rows != 0 && (!is_pow2(strip_rows) || strip_rows < 2 || strip_rows > c->L))
+        return fail(MCRG_ERR_ARG, "strip_rows=%d must be 0 or a power of two in [2, L]", strip_rows);
+    if (fuse_sweeps < 1 || fuse_sweeps > 8) return fail(MCRG_ERR_ARG, "fuse_sweeps=%d must be in [1, 8]", fuse_sweeps);
+    c->strip_rows = strip_rows;
+    c->fuse_sweeps = fuse_sweeps;
+    c->use_graphs = use_graphs;
+    destroy_graphs(c);
+    return 0;
+}
+
+int mcrg_set_couplings(mcrg_ctx *c, const double *K, int n) {
+    if (!c || !K) return fail(MCRG_ERR_ARG, "null pointer");
+    if (n != 1 && n != c->n_replicas) return fail(MCRG_ERR_ARG, "n=%d must be 1 or n_replicas=%d", n, c->n_replicas);
+    CK(cudaSetDevice(c->device));
+    std::vector<uint32_t> t4(c->n_replicas), t8(c->n_replicas), an(c->n_replicas);
+    for (int r = 0; r < c->n_replicas; ++r) {
+        const double k = K[n == 1 ? 0 : r];
+        if (!std::isfinite(k)) return fail(MCRG_ERR_ARG, "coupling %d is not finite", r);
+        // min(1, exp(2 K s h)) with s h in {2, 4}: exp(-4|K|), exp(-8|K|); 32 fractional bits, floor, clamped
+        double p4 = std::floor(std::exp(-4.0 * std::fabs(k)) * 4294967296.0);
+        double p8 = std::floor(std::exp(-8.0 * std::fabs(k)) * 4294967296.0);
+        if (p4 > 4294967295.0) p4 = 4294967295.0;
+        if (p8 > 4294967295.0) p8 = 4294967295.0;
+        t4[r] = (uint32_t)p4;
+        t8[r] = (uint32_t)p8;
+        an[r] = k > 0.0 ? 0xFFFFFFFFu : 0u;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->T4, t4.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->T8, t8.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->anti, an.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int mcrg_init_hot(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    launch_init_hot(c->planes[c->cur], c->L, c->n_replicas, c->seed, c->replica_base, c->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mcrg_init_cold(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    launch_init_cold(c->planes[c->cur], c->L, c->n_replicas, c->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mcrg_set_spins_i32_colmajor(mcrg_ctx *c, int first, int count, const int32_t *host) {
+    if (!c || !host) return fail(MCRG_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
+    CK(cudaSetDevice(c->device));
+    const size_t per = (size_t)c->L * c->L;
+    size_t chunk = ((size_t)256 << 20) / (per * 4);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)count) chunk = count;
+    if (count == 0) return 0;
+    int rc = ensure_stage(c, chunk * per);
+    if (rc) return rc;
+    for (size_t done = 0; done < (size_t)count; done += chunk) {
+        const size_t k = ((size_t)count - done) < chunk ? ((size_t)count - done) : chunk;
+        CK(cudaMemcpyAsync(c->stage, host + done * per, k * per * 4, cudaMemcpyHostToDevice, c->stream));
+        launch_pack0(c->stage, c->planes[c->cur] + (size_t)(first + done) * 2 * c->L * c->W, c->L, (int)k, c->stream);
+        CK(cudaGetLastError());
+        if (done + k < (size_t)count) CK(cudaStreamSynchronize(c->stream));  // staging buffer is reused
+    }
+    return 0;
+}
+
+int mcrg_get_spins_i32_colmajor(mcrg_ctx *c, int first, int count, int32_t *host) {
+    if (!c || !host) return fail(MCRG_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
+    CK(cudaSetDevice(c->device));
+    if (count == 0) return 0;
+    const size_t per = (size_t)c->L * c->L;
+    size_t chunk = ((size_t)256 << 20) / (per * 4);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)count) chunk = count;
+    int rc = ensure_stage(c, chunk * per);
+    if (rc) return rc;
+    for (size_t done = 0; done < (size_t)count; done += chunk) {
+        const size_t k = ((size_t)count - done) < chunk ? ((size_t)count - done) : chunk;
+        launch_unpack0(c->planes[c->cur] + (size_t)(first + done) * 2 * c->L * c->W, c->stage, c->L, (int)k, c->stream);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host + done * per, c->stage, k * per * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *c, int replica, int level, int32_t *host) {
+    if (!c || !host) return fail(MCRG_ERR_ARG, "null pointer");
+    if (replica < 0 || replica >= c->n_replicas) return fail(MCRG_ERR_ARG, "replica %d out of range", replica);
+    if (level < 1 || level > c->last_levels) return fail(MCRG_ERR_STATE, "level %d not produced by the last measurement (levels 1..%d)", level, c->last_levels);
+    CK(cudaSetDevice(c->device));
+    const int Ln = c->L >> level;
+    const size_t per = (size_t)Ln * Ln;
+    int rc = ensure_stage(c, per);
+    if (rc) return rc;
+    launch_unpackN(c->levels + c->level_off[level] + (size_t)replica * Ln * nat_words(Ln), c->stage, Ln, 1, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, c->stage, per * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mcrg_get_sweep_counter(mcrg_ctx *c, uint64_t *t) {
+    if (!c || !t) return fail(MCRG_ERR_ARG, "null pointer");
+    *t = c->t_host;
+    return 0;
+}
+
+int mcrg_set_sweep_counter(mcrg_ctx *c, uint64_t t) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    c->t_host = t;
+    unsigned long long v = t;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->d_t, &v, 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int mcrg_sweep(mcrg_ctx *c, int n_sweeps) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (n_sweeps < 0) return fail(MCRG_ERR_ARG, "n_sweeps=%d < 0", n_sweeps);
+    if (n_sweeps == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    enqueue_sweeps(c, n_sweeps, 0);
+    launch_advance_t(c->d_t, (unsigned long long)n_sweeps, c->stream);
+    c->t_host += (unsigned long long)n_sweeps;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mcrg_measure(mcrg_ctx *c, int max_levels, int64_t *S, int *n_lv_out) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    const int n_lv = clamp_levels(c, max_levels);
+    enqueue_sample(c, n_lv, 0, 0, 0, 0);
+    CK(cudaGetLastError());
+    if (n_lv_out) *n_lv_out = n_lv;
+    if (S) {
+        std::vector<long long> tmp((size_t)c->n_replicas * (MAX_LEVELS + 1) * 4);
+        CK(cudaMemcpyAsync(tmp.data(), c->S_out, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < c->n_replicas; ++r)
+            for (int lv = 0; lv <= n_lv; ++lv)
+                for (int k = 0; k < 4; ++k)
+                    S[((size_t)r * (n_lv + 1) + lv) * 4 + k] = tmp[((size_t)r * (MAX_LEVELS + 1) + lv) * 4 + k];
+    }
+    return 0;
+}
+
+int mcrg_observables(mcrg_ctx *c, int64_t *Snn, int64_t *Snnn, int64_t *Splaq, int64_t *M) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    std::vector<int64_t> S((size_t)c->n_replicas * 4);
+    int rc = mcrg_measure(c, 0, S.data(), nullptr);
+    if (rc) return rc;
+    for (int r = 0; r < c->n_replicas; ++r) {
+        if (Snn) Snn[r] = S[(size_t)r * 4 + 0];
+        if (Snnn) Snnn[r] = S[(size_t)r * 4 + 1];
+        if (Splaq) Splaq[r] = S[(size_t)r * 4 + 2];
+        if (M) M[r] = S[(size_t)r * 4 + 3];
+    }
+    return 0;
+}
+
+int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, int bin) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (n_samples < 0 || sweeps_per_sample < 0) return fail(MCRG_ERR_ARG, "negative count");
+    if (bin < 0 || bin >= c->n_bins) return fail(MCRG_ERR_ARG, "bin %d out of [0, %d)", bin, c->n_bins);
+    if (n_samples == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n_lv = clamp_levels(c, max_levels);
+    const int m = sweeps_per_sample;
+    int done = 0;
+    if (c->use_graphs) {
+        const int chunk = 16;
+        while (n_samples - done >= chunk) {
+            GraphKey key{m, n_lv, bin, chunk, c->cur, c->strip_rows, c->fuse_sweeps};
+            auto it = c->graphs.find(key);
+            const int cur_before = c->cur;
+            if (it == c->graphs.end()) {
+                cudaGraph_t g = nullptr;
+                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m);
+                launch_advance_t(c->d_t, (unsigned long long)chunk * m, c->stream);
+                cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+                if (e != cudaSuccess) {
+                    c->cur = cur_before;
+                    return fail(MCRG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+                }
+                cudaGraphExec_t ge = nullptr;
+                e = cudaGraphInstantiate(&ge, g, 0);
+                cudaGraphDestroy(g);
+                if (e != cudaSuccess) {
+                    c->cur = cur_before;
+                    return fail(MCRG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+                }
+                it = c->graphs.emplace(key, ge).first;
+                // the capture advanced c->cur exactly as a replay will
+            } else {
+                // replay flips the ping-pong index as often as the capture did
+                int flips_per_sample = m > 0 ? 1 : 0;
+                if (m > 1) flips_per_sample += (m - 1 + c->fuse_sweeps - 1) / c->fuse_sweeps;
+                if ((chunk * flips_per_sample) & 1) c->cur ^= 1;
+                c->last_levels = n_lv;
+            }
+            CK(cudaGraphLaunch(it->second, c->stream));
+            c->t_host += (unsigned long long)chunk * m;
+            done += chunk;
+        }
+    }
+    const int rest = n_samples - done;
+    if (rest > 0) {
+        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m);
+        if (m > 0) launch_advance_t(c->d_t, (unsigned long long)rest * m, c->stream);
+        c->t_host += (unsigned long long)rest * m;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mcrg_profile_kernels(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, float *out_ms) {
+    if (!c || !out_ms) return fail(MCRG_ERR_ARG, "null pointer");
+    if (n_samples < 1 || n_samples > 4096 || sweeps_per_sample < 0) return fail(MCRG_ERR_ARG, "bad counts");
+    CK(cudaSetDevice(c->device));
+    const int n_lv = clamp_levels(c, max_levels);
+    const int m = sweeps_per_sample;
+    std::vector<cudaEvent_t> ev((size_t)n_samples * 5);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, &ev[(size_t)s * 5]);
+    if (m > 0) launch_advance_t(c->d_t, (unsigned long long)n_samples * m, c->stream);
+    c->t_host += (unsigned long long)n_samples * m;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    double acc[4] = {0, 0, 0, 0};
+    for (int s = 0; s < n_samples; ++s)
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev[(size_t)s * 5 + k], ev[(size_t)s * 5 + k + 1]));
+            acc[k] += ms;
+        }
+    for (auto &e : ev) cudaEventDestroy(e);
+    out_ms[0] = (float)(acc[0] / n_samples);  // k_sweep0<true>
+    out_ms[1] = (float)(acc[3] / n_samples);  // k_sweep0<false> launches after the measurement
+    out_ms[2] = (float)(acc[1] / n_samples);  // k_level launches
+    out_ms[3] = (float)(acc[2] / n_samples);  // k_tail
+    return 0;
+}
+
+int mcrg_accumulators_layout(mcrg_acc_layout *o) {
+    if (!o) return fail(MCRG_ERR_ARG, "null pointer");
+    o->n_slots = N_SLOTS;
+    o->n_dslots = N_DSLOTS;
+    o->slot_n = SLOT_N;
+    o->slot_absm = SLOT_ABSM;
+    o->slot_m2 = SLOT_M2;
+    o->slot_s = SLOT_S;
+    o->slot_ss = SLOT_SS;
+    o->slot_sbs = SLOT_SBS;
+    o->dslot_m4 = 0;
+    return 0;
+}
+
+int mcrg_accumulators_reset(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    const size_t n_acc = (size_t)c->n_replicas * c->n_bins * N_SLOTS;
+    CK(cudaMemsetAsync(c->acc_lo, 0, n_acc * 8, c->stream));
+    CK(cudaMemsetAsync(c->acc_hi, 0, n_acc * 8, c->stream));
+    CK(cudaMemsetAsync(c->acc_d, 0, (size_t)c->n_replicas * c->n_bins * N_DSLOTS * 8, c->stream));
+    return 0;
+}
+
+int mcrg_accumulators_get(mcrg_ctx *c, int64_t *hi, uint64_t *lo, double *d) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    const size_t n_acc = (size_t)c->n_replicas * c->n_bins * N_SLOTS;
+    if (hi) CK(cudaMemcpyAsync(hi, c->acc_hi, n_acc * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (lo) CK(cudaMemcpyAsync(lo, c->acc_lo, n_acc * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (d) CK(cudaMemcpyAsync(d, c->acc_d, (size_t)c->n_replicas * c->n_bins * N_DSLOTS * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mcrg_accumulators_total_limbs_device(mcrg_ctx *c, void *dev_out) {
+    if (!c || !dev_out) return fail(MCRG_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    launch_total_limbs(c->acc_lo, c->acc_hi, c->n_replicas * c->n_bins, (long long *)dev_out, c->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Kernel-side declarations shared by kernels.cu and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tile.cuh"
+
+namespace mcrg {
+
+constexpr int MAX_LEVELS = 15;          // L <= 2^15; levels 0..14 at most
+constexpr int NOP = 3;                  // even operators: nn, nnn, plaquette
+constexpr int TAIL_MAX_L = 256;         // blocked lattices up to this size finish inside one CTA's shared memory
+constexpr int SWEEP_THREADS = 256;
+
+// accumulator slots (per replica, per bin), all exact 128-bit integers (lo: uint64, hi: int64)
+constexpr int SLOT_N = 0;                                    // samples
+constexpr int SLOT_ABSM = 1;                                 // sum |M|,  M = sum of spins at level 0
+constexpr int SLOT_M2 = 2;                                   // sum M^2
+constexpr int SLOT_S = 3;                                    // + lv*NOP + op          sum S^(lv)_op
+constexpr int SLOT_SS = SLOT_S + NOP * (MAX_LEVELS + 1);     // + lv*9 + b*3 + a        sum S^(lv)_a S^(lv)_b
+constexpr int SLOT_SBS = SLOT_SS + NOP * NOP * (MAX_LEVELS + 1);  // + (n-1)*9 + b*3 + a  sum S^(n)_a S^(n-1)_b
+constexpr int N_SLOTS = SLOT_SBS + NOP * NOP * MAX_LEVELS;
+constexpr int N_DSLOTS = 1;  // double slots: sum M^4
+
+struct SweepArgs {
+    const uint32_t *src;       // planes [replica][colour][y][w]
+    uint32_t *dst;
+    uint32_t *level1;          // natural layout [replica][y][w] of the L/2 lattice (MEASURE only)
+    unsigned long long *cnt;   // [replica][MAX_LEVELS+1][4] raw popcounts (MEASURE only)
+    const uint32_t *T4, *T8, *anti;  // per replica
+    const unsigned long long *d_t;   // device-resident sweep counter
+    unsigned long long t_off;
+    uint64_t seed;
+    uint32_t replica_base;
+    int L, W, bits;
+    int R, H, nsw;
+    int strips;                // L / R
+};
+
+struct LevelArgs {
+    const uint32_t *in;        // natural layout [replica][y][w], lattice size Ln
+    uint32_t *out;             // natural layout of Ln/2 (nullptr: measure only)
+    unsigned long long *cnt;
+    const unsigned long long *d_t;
+    unsigned long long t_off;
+    uint64_t seed;
+    uint32_t replica_base;
+    int Ln, level;             // level index of `in`
+    int R, strips;
+};
+
+struct TailArgs {
+    const uint32_t *in;        // level `start` lattice, natural layout [replica][y][w] (unused if start > n_levels)
+    uint32_t *levels_out;      // base of the level buffers
+    const size_t *level_off;   // [MAX_LEVELS+1] word offset of each level's [replica][y][w] block
+    unsigned long long *cnt;
+    long long *S_out;          // [replica][MAX_LEVELS+1][4] converted sums of the last measurement
+    unsigned long long *acc_lo;
+    long long *acc_hi;
+    double *acc_d;
+    const unsigned long long *d_t;
+    unsigned long long t_off;
+    uint64_t seed;
+    uint32_t replica_base;
+    int L;                     // level-0 size
+    int start;                 // first level handled here (>= 1)
+    int n_levels;              // blocking levels of this measurement (levels 0..n_levels exist)
+    int n_bins, bin;
+    int accumulate;
+};
+
+void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st);
+void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st);
+void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st);
+void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st);
+void launch_advance_t(unsigned long long *d_t, unsigned long long by, cudaStream_t st);
+void launch_init_hot(uint32_t *planes, int L, int n_replicas, uint64_t seed, uint32_t replica_base, cudaStream_t st);
+void launch_init_cold(uint32_t *planes, int L, int n_replicas, cudaStream_t st);
+void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas, cudaStream_t st);
+void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st);
+void launch_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int n_replicas, cudaStream_t st);
+size_t sweep0_smem_bytes(int L, int R, int H);
+int sweep0_max_smem();
+
+}  // namespace mcrg

@@ -1,0 +1,258 @@
+// CPU emulation of the CUDA kernels' strip logic.  TEST INFRASTRUCTURE ONLY (never part of the product).
+//
+// mcrg_b200/csrc/{bitops,tile}.cuh hold the per-word device functions as host/device code.  This file walks
+// them with the same strip / halo / phase structure as kernels.cu (k_sweep0, k_level, k_tail), "shared memory"
+// being a std::vector, so that the bit tricks, the halo recomputation and the Philox keying can be checked
+// against the oracle on a machine without a GPU.  What it cannot cover — staging, reductions, atomics, launch
+// geometry — is covered by the -m gpu tests on the real kernels.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../mcrg_b200/csrc/tile.cuh"
+
+using namespace mcrg;
+
+namespace {
+
+constexpr int MAX_LEVELS = 15;
+constexpr int TAIL_MAX_L = 256;
+
+struct Emu {
+    int L, W, bits;
+    uint64_t seed;
+    uint32_t replica;
+    std::vector<uint32_t> planes[2];
+    int cur = 0;
+    std::vector<std::vector<uint32_t>> levels;  // [lv] natural layout
+    unsigned long long cnt[MAX_LEVELS + 1][4];
+    McParams mc;
+    uint64_t t = 0;
+};
+
+void sweep0(Emu &e, int R, int nsw, bool measure) {
+    const int L = e.L, W = e.W, H = nsw > 0 ? 2 * nsw : 2, rows = R + 2 * H;
+    const std::vector<uint32_t> &src = e.planes[e.cur];
+    std::vector<uint32_t> &dst = e.planes[1 - e.cur];
+    std::vector<uint32_t> smem((size_t)2 * rows * W);
+    for (int strip = 0; strip < L / R; ++strip) {
+        const int y0 = strip * R;
+        Strip0 s;
+        s.base = smem.data();
+        s.rows = rows;
+        s.W = W;
+        s.bits = e.bits;
+        s.mask = valid_mask(e.bits);
+        s.L = L;
+        s.y_first = (y0 - H) & (L - 1);
+        for (int c = 0; c < 2; ++c)
+            for (int lr = 0; lr < rows; ++lr) {
+                const int y = (s.y_first + lr) & (L - 1);
+                for (int w = 0; w < W; ++w) smem[((size_t)c * rows + lr) * W + w] = src[((size_t)c * L + y) * W + w];
+            }
+        if (measure) {
+            Counts c = {0, 0, 0, 0};
+            for (int i = 0; i < R / 2; ++i)
+                for (int w = 0; w < W; ++w) {
+                    uint32_t maj, tie;
+                    measure_pair0(s, H + 2 * i, w, c, maj, tie);
+                    const uint32_t q = (uint32_t)((y0 / 2 + i) * W + w);
+                    uint32_t out = maj;
+                    if (tie) out |= tie & tie_word(e.seed, q, e.replica, e.t, 1);
+                    e.levels[1][q] = out;
+                }
+            e.cnt[0][0] += c.anti_nn;
+            e.cnt[0][1] += c.anti_nnn;
+            e.cnt[0][2] += c.odd_plaq;
+            e.cnt[0][3] += c.up;
+        }
+        if (nsw > 0) {
+            for (int h = 0; h < 2 * nsw; ++h) {
+                const int c = h & 1;
+                for (int lr = 1 + h; lr < rows - 1 - h; ++lr)
+                    for (int w = 0; w < W; ++w) update_word0(s, c, lr, w, e.mc, e.replica, e.t + (uint64_t)(h >> 1));
+            }
+            for (int c = 0; c < 2; ++c)
+                for (int lr = 0; lr < R; ++lr)
+                    for (int w = 0; w < W; ++w)
+                        dst[((size_t)c * L + y0 + lr) * W + w] = smem[((size_t)c * rows + H + lr) * W + w];
+        }
+    }
+    if (nsw > 0) {
+        e.cur ^= 1;
+    }
+}
+
+void level_strips(Emu &e, int lv, int R, bool do_block) {
+    const int Ln = e.L >> lv, Wn = nat_words(Ln);
+    const std::vector<uint32_t> &in = e.levels[lv];
+    std::vector<uint32_t> smem((size_t)(R + 1) * Wn);
+    for (int strip = 0; strip < Ln / R; ++strip) {
+        const int y0 = strip * R;
+        for (int lr = 0; lr <= R; ++lr)
+            for (int w = 0; w < Wn; ++w) smem[(size_t)lr * Wn + w] = in[(size_t)((y0 + lr) & (Ln - 1)) * Wn + w];
+        StripN s;
+        s.x = smem.data();
+        s.W = Wn;
+        s.bits = nat_bits(Ln);
+        s.mask = valid_mask(s.bits);
+        Counts c = {0, 0, 0, 0};
+        for (int lr = 0; lr < R; ++lr)
+            for (int w = 0; w < Wn; ++w) measure_rowN(s, lr, lr + 1, w, c);
+        if (do_block) {
+            const int Lb = Ln / 2, Wb = nat_words(Lb);
+            for (int i = 0; i < R / 2; ++i)
+                for (int wb = 0; wb < Wb; ++wb) {
+                    uint32_t maj, tie;
+                    block_pairN(s, 2 * i, wb, maj, tie);
+                    const uint32_t q = (uint32_t)((y0 / 2 + i) * Wb + wb);
+                    uint32_t o = maj;
+                    if (tie) o |= tie & tie_word(e.seed, q, e.replica, e.t, lv + 1);
+                    e.levels[lv + 1][q] = o;
+                }
+        }
+        e.cnt[lv][0] += c.anti_nn;
+        e.cnt[lv][1] += c.anti_nnn;
+        e.cnt[lv][2] += c.odd_plaq;
+        e.cnt[lv][3] += c.up;
+    }
+}
+
+void tail(Emu &e, int start, int n_levels) {
+    for (int lv = start; lv <= n_levels; ++lv) {
+        const int Ln = e.L >> lv, Wn = nat_words(Ln);
+        StripN s;
+        s.x = e.levels[lv].data();
+        s.W = Wn;
+        s.bits = nat_bits(Ln);
+        s.mask = valid_mask(s.bits);
+        Counts c = {0, 0, 0, 0};
+        for (int lr = 0; lr < Ln; ++lr)
+            for (int w = 0; w < Wn; ++w) measure_rowN(s, lr, lr + 1 == Ln ? 0 : lr + 1, w, c);
+        e.cnt[lv][0] += c.anti_nn;
+        e.cnt[lv][1] += c.anti_nnn;
+        e.cnt[lv][2] += c.odd_plaq;
+        e.cnt[lv][3] += c.up;
+        if (lv < n_levels) {
+            const int Lb = Ln / 2, Wb = nat_words(Lb);
+            for (int yb = 0; yb < Lb; ++yb)
+                for (int wb = 0; wb < Wb; ++wb) {
+                    uint32_t maj, tie;
+                    block_pairN(s, 2 * yb, wb, maj, tie);
+                    const uint32_t q = (uint32_t)(yb * Wb + wb);
+                    uint32_t o = maj;
+                    if (tie) o |= tie & tie_word(e.seed, q, e.replica, e.t, lv + 1);
+                    e.levels[lv + 1][q] = o;
+                }
+        }
+    }
+}
+
+void pack0(Emu &e, const int32_t *spins) {
+    const int L = e.L, W = e.W;
+    std::vector<uint32_t> &pl = e.planes[e.cur];
+    std::fill(pl.begin(), pl.end(), 0u);
+    for (int y = 0; y < L; ++y)
+        for (int x = 0; x < L; ++x)
+            if (spins[(size_t)y * L + x] > 0) {
+                const int c = (x + y) & 1, xh = x >> 1;
+                pl[((size_t)c * L + y) * W + (xh >> 5)] |= 1u << (xh & 31);
+            }
+}
+
+void unpack0(const Emu &e, int32_t *spins) {
+    const int L = e.L, W = e.W;
+    const std::vector<uint32_t> &pl = e.planes[e.cur];
+    for (int y = 0; y < L; ++y)
+        for (int x = 0; x < L; ++x) {
+            const int c = (x + y) & 1, xh = x >> 1;
+            spins[(size_t)y * L + x] = ((pl[((size_t)c * L + y) * W + (xh >> 5)] >> (xh & 31)) & 1u) ? 1 : -1;
+        }
+}
+
+Emu make(int L, uint64_t seed, uint32_t replica, uint32_t T4, uint32_t T8, uint32_t anti, uint64_t t) {
+    Emu e;
+    e.L = L;
+    e.W = l0_words(L);
+    e.bits = l0_bits(L);
+    e.seed = seed;
+    e.replica = replica;
+    e.planes[0].assign((size_t)2 * L * e.W, 0u);
+    e.planes[1].assign((size_t)2 * L * e.W, 0u);
+    e.levels.resize(MAX_LEVELS + 1);
+    for (int lv = 1; (L >> lv) >= 2; ++lv) e.levels[lv].assign((size_t)(L >> lv) * nat_words(L >> lv), 0u);
+    std::memset(e.cnt, 0, sizeof e.cnt);
+    e.mc.seed = seed;
+    e.mc.T4 = T4;
+    e.mc.T8 = T8;
+    e.mc.anti = anti;
+    e.t = t;
+    return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+// n_sweeps Metropolis sweeps with strips of R rows and `fuse` sweeps per pass, exactly as mcrg_sweep() sequences
+// k_sweep0<false>; spins in/out in the reference layout.
+void emul_sweep(int L, int32_t *spins, int R, int fuse, int n_sweeps, uint64_t seed, uint32_t replica, uint32_t T4,
+                uint32_t T8, uint32_t anti, uint64_t t0) {
+    Emu e = make(L, seed, replica, T4, T8, anti, t0);
+    pack0(e, spins);
+    int done = 0;
+    while (done < n_sweeps) {
+        const int k = (n_sweeps - done) < fuse ? (n_sweeps - done) : fuse;
+        e.t = t0 + done;
+        sweep0(e, R, k, false);
+        done += k;
+    }
+    unpack0(e, spins);
+}
+
+// One measurement as enqueue_sample() sequences it (k_sweep0<true> with nsw sweeps fused, k_level while the
+// blocked lattice is larger than TAIL_MAX_L, k_tail): S[(lv)*4+k], packed levels unpacked to level_spins
+// (concatenated, reference layout), spins updated in place if nsw > 0.  Returns the number of levels.
+int emul_measure(int L, int32_t *spins, int R, int Rn, int nsw, int max_levels, uint64_t seed, uint32_t replica,
+                 uint32_t T4, uint32_t T8, uint32_t anti, uint64_t t, int64_t *S, int32_t *level_spins) {
+    Emu e = make(L, seed, replica, T4, T8, anti, t);
+    pack0(e, spins);
+    int n_lv = 0;
+    while ((L >> (n_lv + 1)) >= 2) ++n_lv;  // log2(L) - 1
+    if (max_levels >= 0 && max_levels < n_lv) n_lv = max_levels;
+    sweep0(e, R, nsw, true);
+    int lv = 1;
+    while (lv <= n_lv && (L >> lv) > TAIL_MAX_L) {
+        const int Ln = L >> lv;
+        level_strips(e, lv, Rn < Ln ? Rn : Ln, lv < n_lv);
+        ++lv;
+    }
+    tail(e, lv, n_lv);
+    for (int k = 0; k <= n_lv; ++k) {
+        long long s4[4];
+        counts_to_S((long long)(L >> k), e.cnt[k][0], e.cnt[k][1], e.cnt[k][2], e.cnt[k][3], s4);
+        for (int j = 0; j < 4; ++j) S[k * 4 + j] = s4[j];
+    }
+    if (level_spins) {
+        size_t off = 0;
+        for (int k = 1; k <= n_lv; ++k) {
+            const int Ln = L >> k, Wn = nat_words(Ln);
+            for (int y = 0; y < Ln; ++y)
+                for (int x = 0; x < Ln; ++x)
+                    level_spins[off + (size_t)y * Ln + x] = ((e.levels[k][(size_t)y * Wn + (x >> 5)] >> (x & 31)) & 1u) ? 1 : -1;
+            off += (size_t)Ln * Ln;
+        }
+    }
+    if (nsw > 0) unpack0(e, spins);
+    return n_lv;
+}
+
+void emul_hot_start(int L, uint64_t seed, uint32_t replica, int32_t *spins) {
+    Emu e = make(L, seed, replica, 0, 0, 0, 0);
+    const int W = e.W;
+    for (size_t idx = 0; idx < (size_t)2 * L * W; ++idx)
+        e.planes[0][idx] = philox_keyed(seed, (uint32_t)idx, replica, 0ull, PURPOSE_INIT, 0).x & valid_mask(e.bits);
+    unpack0(e, spins);
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+"""GPU parity tests: the CUDA library (through its C ABI) against the CPU oracle on the same inputs and the same
+Philox keys.  Integer / bit work => bit-exact.  Run on the B200 box: pytest -m gpu.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _libs
+
+pytestmark = pytest.mark.gpu
+
+KC = -0.5 * np.log(1 + np.sqrt(2))
+
+
+@pytest.fixture(scope="module")
+def mc():
+    import mcrg_b200
+
+    # the product must be the CUDA path: fail loudly if the library or the device is missing
+    assert mcrg_b200.capi.device_count() >= 1
+    return mcrg_b200
+
+
+def oracle_hot(L, seed, replica):
+    s = np.zeros((L, L), np.int32)
+    _libs.oracle().orc_hot_start(L, seed, replica, s)
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------
+# transport and initial conditions
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("L,R", [(4, 3), (8, 5), (16, 2), (32, 3), (64, 4), (128, 3), (256, 2), (1024, 2)])
+def test_pack_unpack_roundtrip(mc, L, R):
+    spins = np.stack([_libs.random_lattice(L, 10 + r) for r in range(R)])
+    with mc.Context(L, R) as ctx:
+        ctx.set_spins(spins)
+        assert np.array_equal(ctx.get_spins(), spins)
+        # partial range
+        ctx.set_spins(-spins[:1], first=R - 1)
+        got = ctx.get_spins()
+        assert np.array_equal(got[R - 1], -spins[0])
+        assert np.array_equal(got[: R - 1], spins[: R - 1])
+
+
+@pytest.mark.parametrize("L", [4, 8, 32, 64, 128, 512])
+def test_hot_start_matches_oracle(mc, L):
+    with mc.Context(L, 3, seed=777, replica_base=5) as ctx:
+        ctx.init_hot()
+        got = ctx.get_spins()
+        for r in range(3):
+            assert np.array_equal(got[r], oracle_hot(L, 777, 5 + r))
+        ctx.init_cold()
+        assert (ctx.get_spins() == 1).all()
+
+
+def test_bad_arguments_are_reported(mc):
+    for L in (0, 3, 6, 100, 32768):
+        with pytest.raises(mc.McrgError):
+            mc.Context(L, 1)
+    with pytest.raises(mc.McrgError):
+        mc.Context(8, 0)
+    with mc.Context(8, 2) as ctx:
+        with pytest.raises(mc.McrgError):
+            ctx.set_spins(np.ones((3, 8, 8), np.int32))
+        with pytest.raises(mc.McrgError):
+            ctx.get_level_spins(0, 1)  # nothing measured yet
+        with pytest.raises(mc.McrgError):
+            ctx.run(1, 1, -1, bin=1)
+        with pytest.raises(mc.McrgError):
+            ctx.set_couplings([KC, KC, KC])
+        with pytest.raises(mc.McrgError):
+            ctx.set_tuning(strip_rows=3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# deterministic observables, block spins, pyramid   (bit-exact)
+# ---------------------------------------------------------------------------------------------------------
+
+def lattice_cases(L):
+    cases = dict(_libs.pattern_lattices(L))
+    cases["rand0"] = _libs.random_lattice(L, 1)
+    cases["rand1"] = _libs.random_lattice(L, 2)
+    cases["biased"] = _libs.random_lattice(L, 3, p_up=0.8)
+    if L <= 256:
+        cases["clustered"] = _libs.clustered_lattice(L, 4, n_sweeps=10)
+    return cases
+
+
+@pytest.mark.parametrize("L", [4, 8, 16, 32, 64, 128, 256, 512, 1024])
+def test_observables_match_oracle(mc, L):
+    o = _libs.oracle()
+    cases = lattice_cases(L)
+    spins = np.stack(list(cases.values()))
+    with mc.Context(L, len(cases)) as ctx:
+        ctx.set_spins(spins)
+        obs = ctx.observables()
+    for r, (name, s) in enumerate(cases.items()):
+        want = np.zeros(2, np.int64)
+        o.orc_calc_interactions(L, s, want)
+        assert obs["Snn"][r] == want[0], (L, name)
+        assert obs["Snnn"][r] == want[1], (L, name)
+        assert obs["Splaq"][r] == o.orc_plaquette(L, s), (L, name)
+        assert obs["M"][r] == int(s.sum()), (L, name)
+
+
+@pytest.mark.parametrize("L,strip", [(4, 0), (8, 2), (16, 0), (32, 8), (64, 0), (128, 16), (256, 0), (512, 0), (1024, 0),
+                                     (2048, 32)])
+def test_pyramid_matches_oracle(mc, L, strip):
+    seed, base, t = 4242, 9, (1 << 34) + 17
+    cases = lattice_cases(L)
+    if L >= 1024:
+        cases = {k: cases[k] for k in ("rand0", "checker", "stripes_i")}
+    spins = np.stack(list(cases.values()))
+    with mc.Context(L, len(cases), seed=seed, replica_base=base) as ctx:
+        ctx.set_tuning(strip_rows=strip)
+        ctx.set_spins(spins)
+        ctx.sweep_counter = t
+        S = ctx.measure()
+        n_lv = S.shape[1] - 1
+        assert n_lv == int(np.log2(L)) - 1
+        for r, (name, s) in enumerate(cases.items()):
+            want_S, want_lv = _libs.pyramid(L, s, seed, base + r, t, -1, want_levels=True)
+            assert np.array_equal(S[r], want_S), (L, name, S[r], want_S)
+            for k in range(1, n_lv + 1):
+                assert np.array_equal(ctx.get_level_spins(r, k), want_lv[k - 1]), (L, name, k)
+        # the configuration itself is untouched by a measurement
+        assert np.array_equal(ctx.get_spins(), spins)
+        # capped pyramid
+        S3 = ctx.measure(max_levels=min(2, n_lv))
+        assert np.array_equal(S3, S[:, : min(2, n_lv) + 1])
+
+
+def test_golden_reference_vectors(mc):
+    """Correlators / energy / magnetisation / non-tie block spins produced by the reference itself
+    (tests/golden/deterministic.npz, made by tests/golden/make_golden.py from the compiled reference)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "deterministic.npz"))
+    by_N = {}
+    for key in g["index"]:
+        N = int(str(key).split("_")[0][1:])
+        by_N.setdefault(N, []).append(str(key))
+    for N, keys in by_N.items():
+        if N < 4:
+            continue  # contexts start at L = 4; the 2x2 lattice is reached as the last pyramid level
+        spins = np.stack([np.where(np.unpackbits(g[k + "_bits"])[: N * N].reshape(N, N) > 0, 1, -1) for k in keys]).astype(np.int32)
+        with mc.Context(N, len(keys), seed=1) as ctx:
+            ctx.set_spins(spins)
+            obs = ctx.observables()
+            ctx.measure(max_levels=1)
+            for r, k in enumerate(keys):
+                ref = g[k + "_ref"]
+                assert obs["Snn"][r] == ref[0] and obs["Snnn"][r] == ref[1] and obs["Snn"][r] == ref[2], k
+                assert obs["M"][r] == ref[5], k
+                # IsingModel::calc_energy = K*S_nn/N^2 up to the reference's own rounding (ising.cpp:160-172)
+                assert abs(KC * obs["Snn"][r] / (N * N) - ref[3]) <= 1e-12 * max(1.0, abs(ref[3])), k
+                # IsingModel::calc_magnetization: integer division (ising.cpp:178)
+                assert float(int(obs["M"][r] / (N * N))) == ref[4], k
+                want_blk = np.where(np.unpackbits(g[k + "_block_bits"])[: (N // 2) ** 2].reshape(N // 2, N // 2) > 0, 1, -1)
+                got_blk = ctx.get_level_spins(r, 1)
+                nontie = spins[r].reshape(N // 2, 2, N // 2, 2).sum(axis=(1, 3)) != 0
+                assert np.array_equal(got_blk[nontie], want_blk[nontie]), k
+
+
+def test_tie_coins_are_fair_and_keyed(mc):
+    L = 256
+    s = _libs.pattern_lattices(L)["stripes_i"]  # every 2x2 block ties
+    with mc.Context(L, 2, seed=31337) as ctx:
+        ctx.set_spins(np.stack([s, s]))
+        ctx.measure(max_levels=1)
+        a0, a1 = ctx.get_level_spins(0, 1), ctx.get_level_spins(1, 1)
+        ctx.measure(max_levels=1)
+        assert np.array_equal(a0, ctx.get_level_spins(0, 1))  # same key -> same coins
+        assert (a0 != a1).mean() > 0.4  # other replica -> other coins
+        ctx.sweep_counter = 5
+        ctx.measure(max_levels=1)
+        assert (a0 != ctx.get_level_spins(0, 1)).mean() > 0.4  # other time -> other coins
+        n = a0.size
+        assert abs((a0 == 1).sum() - n / 2) < 5 * np.sqrt(n) / 2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Metropolis trajectories   (bit-exact against the scalar specification with the same Philox keys)
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("L,strip,fuse,n_sweeps", [(4, 0, 1, 3), (8, 2, 1, 4), (16, 0, 2, 5), (32, 8, 1, 3), (64, 0, 1, 4),
+                                                   (64, 16, 3, 7), (128, 0, 2, 3), (256, 32, 1, 2), (512, 0, 1, 2),
+                                                   (1024, 16, 2, 2)])
+def test_sweeps_match_scalar_metropolis(mc, L, strip, fuse, n_sweeps):
+    o = _libs.oracle()
+    seed, base, t0 = 0xABCDEF0123, 3, (1 << 32) - 2  # crosses the 32-bit boundary of the sweep counter
+    Ks = np.array([KC, -0.3, 0.35])
+    R = len(Ks)
+    with mc.Context(L, R, seed=seed, replica_base=base) as ctx:
+        ctx.set_tuning(strip_rows=strip, fuse_sweeps=fuse)
+        ctx.set_couplings(Ks)
+        ctx.init_hot()
+        ctx.sweep_counter = t0
+        ctx.sweep(n_sweeps)
+        assert ctx.sweep_counter == t0 + n_sweeps
+        got = ctx.get_spins()
+        # continuing in two calls gives the same chain as one call
+        ctx.sweep(2)
+        got2 = ctx.get_spins()
+    for r in range(R):
+        want = oracle_hot(L, seed, base + r)
+        o.orc_metropolis(L, want, Ks[r], seed, base + r, t0, n_sweeps)
+        assert np.array_equal(got[r], want), (L, r)
+        o.orc_metropolis(L, want, Ks[r], seed, base + r, t0 + n_sweeps, 2)
+        assert np.array_equal(got2[r], want), (L, r)
+
+
+def test_sweep_is_independent_of_strip_geometry_at_full_size(mc):
+    """L = 4096 and 16384: the oracle is too slow for many sweeps, so use the size-independent property that the
+    result cannot depend on the strip height or on how many sweeps are fused per launch (halo recomputation with
+    counter-based random numbers), plus one exact oracle sweep at 4096."""
+    o = _libs.oracle()
+    for L, variants in ((4096, [(0, 1), (8, 1), (64, 2), (16, 3)]), (16384, [(0, 1), (8, 2), (32, 1)])):
+        results = []
+        for strip, fuse in variants:
+            with mc.Context(L, 1, seed=99) as ctx:
+                ctx.set_tuning(strip_rows=strip, fuse_sweeps=fuse)
+                ctx.init_hot()
+                ctx.sweep(3)
+                obs = ctx.observables()
+                results.append((obs, ctx.get_spins() if L == 4096 else None))
+        for obs, spins in results[1:]:
+            for k in ("Snn", "Snnn", "Splaq", "M"):
+                assert obs[k][0] == results[0][0][k][0], (L, k)
+            if spins is not None:
+                assert np.array_equal(spins, results[0][1])
+        if L == 4096:
+            want = oracle_hot(L, 99, 0)
+            o.orc_metropolis(L, want, KC, 99, 0, 0, 1)
+            with mc.Context(L, 1, seed=99) as ctx:
+                ctx.init_hot()
+                ctx.sweep(1)
+                assert np.array_equal(ctx.get_spins()[0], want)
+
+
+def test_full_size_pyramid_properties(mc):
+    """L = 16384 (config C5: 8 levels) and 4096 (11 levels): exact known answers for ordered configurations and
+    the oracle on a random one at 4096."""
+    for L in (4096, 16384):
+        jj, ii = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
+        S = []
+        with mc.Context(L, 1, seed=5) as ctx:
+            for name in ("up", "checker", "stripes_i"):
+                if name == "up":
+                    s = np.ones((L, L), np.int32)
+                elif name == "checker":
+                    s = (1 - 2 * ((ii + jj) & 1)).astype(np.int32)
+                else:
+                    s = (1 - 2 * (ii & 1)).astype(np.int32)
+                ctx.set_spins(s[None])
+                S.append(ctx.measure(max_levels=8)[0])
+                del s
+        del jj, ii
+        S = np.stack(S)
+        n2 = np.array([(L >> k) ** 2 for k in range(9)], np.int64)
+        # all up: every level all up
+        assert np.array_equal(S[0, :, 0], 4 * n2) and np.array_equal(S[0, :, 1], 4 * n2)
+        assert np.array_equal(S[0, :, 2], n2) and np.array_equal(S[0, :, 3], n2)
+        # checkerboard: level 0 is the Neel state; every block ties
+        assert S[1, 0, 0] == -4 * n2[0] and S[1, 0, 1] == 4 * n2[0] and S[1, 0, 2] == n2[0] and S[1, 0, 3] == 0
+        # stripes along i: nn = 0 (2 aligned + 2 anti), nnn = -4 n^2, plaquettes all +1
+        assert S[2, 0, 0] == 0 and S[2, 0, 1] == -4 * n2[0] and S[2, 0, 2] == n2[0] and S[2, 0, 3] == 0
+    L = 4096
+    s = _libs.random_lattice(L, 8)
+    with mc.Context(L, 1, seed=6, replica_base=2) as ctx:
+        ctx.set_spins(s[None])
+        S = ctx.measure()
+    assert np.array_equal(S[0], _libs.pyramid(L, s, 6, 2, 0, -1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the sample loop and its accumulators   (exact 128-bit integers)
+# ---------------------------------------------------------------------------------------------------------
+
+def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start):
+    """mcrg_run's contract restated with the oracle: per sample measure (pyramid with Philox ties keyed by the
+    sweep counter), accumulate (mcrg.cpp:86-97, exact), then m sweeps."""
+    o = _libs.oracle()
+    s = start.copy()
+    n_lv = o.orc_n_transformations(L, 2)
+    if 0 <= max_levels < n_lv:
+        n_lv = max_levels
+    S_sum = np.zeros((n_lv + 1) * 3, np.int64)
+    SS = [[0] * 9 for _ in range(n_lv + 1)]
+    hi1 = np.zeros(n_lv * 9, np.int64); lo1 = np.zeros(n_lv * 9, np.uint64)
+    hi2 = np.zeros(n_lv * 9, np.int64); lo2 = np.zeros(n_lv * 9, np.uint64)
+    absM = M2 = 0
+    M4 = 0.0
+    t = t0
+    for _ in range(n_samples):
+        S4 = _libs.pyramid(L, s, seed, replica, t, max_levels)
+        S3 = np.ascontiguousarray(S4[:, :3])
+        o.orc_accumulate_i128(n_lv, 3, S3.ravel(), S_sum, hi1, lo1, hi2, lo2)
+        for lv in range(n_lv + 1):
+            for b in range(3):
+                for a in range(3):
+                    SS[lv][b * 3 + a] += int(S3[lv, a]) * int(S3[lv, b])
+        M = int(S4[0, 3])
+        absM += abs(M); M2 += M * M; M4 += float(M) ** 4
+        o.orc_metropolis(L, s, K, seed, replica, t, m)
+        t += m
+    SbS = [int(h) * (1 << 64) + int(l) for h, l in zip(hi1, lo1)]
+    SbSb = [int(h) * (1 << 64) + int(l) for h, l in zip(hi2, lo2)]
+    return dict(n=n_samples, absM=absM, M2=M2, M4=M4, S=S_sum, SS=SS, SbS=SbS, SbSb=SbSb, final=s, n_lv=n_lv)
+
+
+@pytest.mark.parametrize("L,n_samples,m,max_levels,graphs", [(8, 5, 1, -1, 0), (16, 20, 2, -1, 1), (64, 37, 1, -1, 1),
+                                                            (64, 6, 3, 2, 0), (128, 18, 1, -1, 1), (512, 3, 1, -1, 0),
+                                                            (1024, 2, 2, 4, 0)])
+def test_run_accumulators_match_oracle(mc, L, n_samples, m, max_levels, graphs):
+    seed, base, t0 = 2024, 1, 1000
+    Ks = [KC, -0.42]
+    lay = mc.capi.acc_layout()
+    with mc.Context(L, 2, seed=seed, replica_base=base, n_bins=2) as ctx:
+        ctx.set_tuning(use_graphs=graphs)
+        ctx.set_couplings(Ks)
+        ctx.init_hot()
+        ctx.sweep_counter = t0
+        ctx.run(n_samples, m, max_levels, bin=1)
+        acc, accd = ctx.accumulators()
+        final = ctx.get_spins()
+        limbs_host = None
+        try:
+            import torch
+
+            limbs = torch.zeros(lay.n_slots * 4, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()
+            ctx.total_limbs_to_device(limbs.data_ptr())
+            ctx.sync()
+            limbs_host = limbs.cpu().numpy()
+        except ImportError:
+            pass
+    assert (acc[:, 0, :] == 0).all()  # bin 0 untouched
+    for r in range(2):
+        want = cpu_run(L, seed, base + r, Ks[r], t0, n_samples, m, max_levels, oracle_hot(L, seed, base + r))
+        n_lv = want["n_lv"]
+        a = acc[r, 1]
+        assert a[lay.slot_n] == want["n"]
+        assert a[lay.slot_absm] == want["absM"] and a[lay.slot_m2] == want["M2"]
+        assert abs(accd[r, 1, lay.dslot_m4] - want["M4"]) <= 1e-12 * max(1.0, want["M4"])
+        for lv in range(n_lv + 1):
+            for op in range(3):
+                assert a[lay.slot_s + lv * 3 + op] == int(want["S"][lv * 3 + op]), (r, lv, op)
+            for e in range(9):
+                assert a[lay.slot_ss + lv * 9 + e] == want["SS"][lv][e], (r, lv, e)
+        for n in range(n_lv):
+            for e in range(9):
+                assert a[lay.slot_sbs + n * 9 + e] == want["SbS"][n * 9 + e], (r, n, e)
+                assert a[lay.slot_ss + (n + 1) * 9 + e] == want["SbSb"][n * 9 + e], (r, n, e)  # Sb_Sb == SS of level n+1
+        # slots of levels that do not exist stay zero
+        for lv in range(n_lv + 1, mc.capi.MAX_LEVELS + 1):
+            assert all(a[lay.slot_s + lv * 3 + op] == 0 for op in range(3))
+        assert np.array_equal(final[r], want["final"]), (L, r)
+    if limbs_host is not None:
+        tot = mc.dist.limbs_to_ints(limbs_host)
+        assert tot == [int(x) for x in acc.sum(axis=(0, 1))]
+
+
+def test_products_beyond_int64(mc):
+    """L = 16384, all spins up: S_nn = 4 L^2 = 2^30, so S(1) x S(0) ~ 2^58 per sample; 64 samples overflow int64
+    (2^63) — the 128-bit accumulators must hold the exact value."""
+    L, n = 16384, 64
+    lay = mc.capi.acc_layout()
+    with mc.Context(L, 1, seed=1) as ctx:
+        ctx.init_cold()
+        ctx.run(n, 0, 1, 0)  # measure only: configuration stays all-up
+        acc, _ = ctx.accumulators()
+    a = acc[0, 0]
+    s0, s1 = 4 * L * L, 4 * (L // 2) ** 2
+    assert a[lay.slot_n] == n
+    assert a[lay.slot_s + 0] == n * s0 and a[lay.slot_s + 3] == n * s1
+    assert a[lay.slot_ss + 0] == n * s0 * s0 and n * s0 * s0 > 2**63
+    assert a[lay.slot_sbs + 0] == n * s1 * s0
+    assert a[lay.slot_m2] == n * (L * L) ** 2
