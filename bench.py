@@ -311,6 +311,9 @@ def run_ours(args, rank, world, local_rank):
                                           f"(Wolff update + correlators at all levels), each sample counted as L^2 attempts; loop {loop:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    # release everything that was used on the context's stream before the stream is destroyed
+    del host, host_np, result, limbs, e0, e1
+    torch.cuda.synchronize()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

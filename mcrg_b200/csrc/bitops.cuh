@@ -40,6 +40,17 @@ MCRG_HD int popc32(uint32_t v) {
 MCRG_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
+#if defined(__CUDA_ARCH__) && !defined(MCRG_PHILOX_NO_PTX)  // explicit mul.wide + unpack: fewer register-pair moves
+        uint32_t h0, l0, h1, l1;
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1,%0}, p;\n\t}" : "=r"(h0), "=r"(l0) : "r"(0xD2511F53u), "r"(c0));
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1,%0}, p;\n\t}" : "=r"(h1), "=r"(l1) : "r"(0xCD9E8D57u), "r"(c2));
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
+        c0 = n0;
+        c2 = n2;
+#else
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -48,6 +59,7 @@ MCRG_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
         c3 = (uint32_t)p0;
         c0 = n0;
         c2 = n2;
+#endif
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }

@@ -80,7 +80,7 @@ namespace {
 int choose_R(const mcrg_ctx *c, int H) {
     const int L = c->L, W = c->W;
     const int max_smem = sweep0_max_smem();
-    auto fits = [&](int R) { return (long long)sweep0_smem_bytes(L, R, H) <= (long long)max_smem - 1024; };
+    auto fits = [&](int R) { return (long long)sweep0_smem_bytes(L, R, H) <= (long long)max_smem; };
     if (c->strip_rows >= 2 && c->strip_rows <= L && is_pow2(c->strip_rows) && fits(c->strip_rows)) return c->strip_rows;
     int R = 4096 / W;
     if (R > 64) R = 64;

@@ -36,17 +36,17 @@ __device__ __forceinline__ void warp_reduce_to(const Counts &c, unsigned int *ce
 // rows [row_lo, row_lo+nrows) of a [*, W] word array: global -> shared, periodic in y (L a power of two)
 __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W,
                                            int L) {
-    if ((W & 3) == 0) {
-        const int W4 = W >> 2, n4 = nrows * W4;
+    if ((W & 3) == 0) {  // W is a power of two: shifts, not divisions
+        const int W4 = W >> 2, l4 = ilog2(W4), n4 = nrows << l4;
         for (int idx = threadIdx.x; idx < n4; idx += blockDim.x) {
-            const int lr = idx / W4, w4 = idx - lr * W4;
+            const int lr = idx >> l4, w4 = idx & (W4 - 1);
             const int y = (y_first + lr) & (L - 1);
             reinterpret_cast<uint4 *>(dst)[idx] = __ldg(reinterpret_cast<const uint4 *>(src_plane + (size_t)y * W) + w4);
         }
     } else {
-        const int n = nrows * W;
+        const int lw = ilog2(W), n = nrows << lw;
         for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            const int lr = idx / W, w = idx - lr * W;
+            const int lr = idx >> lw, w = idx & (W - 1);
             const int y = (y_first + lr) & (L - 1);
             dst[idx] = __ldg(src_plane + (size_t)y * W + w);
         }
@@ -56,26 +56,142 @@ __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_pl
 __device__ __forceinline__ void unstage_rows(uint32_t *dst_plane, const uint32_t *src, int y_first, int nrows, int W,
                                              int L) {
     if ((W & 3) == 0) {
-        const int W4 = W >> 2, n4 = nrows * W4;
+        const int W4 = W >> 2, l4 = ilog2(W4), n4 = nrows << l4;
         for (int idx = threadIdx.x; idx < n4; idx += blockDim.x) {
-            const int lr = idx / W4, w4 = idx - lr * W4;
+            const int lr = idx >> l4, w4 = idx & (W4 - 1);
             const int y = (y_first + lr) & (L - 1);
             reinterpret_cast<uint4 *>(dst_plane + (size_t)y * W)[w4] = reinterpret_cast<const uint4 *>(src)[idx];
         }
     } else {
-        const int n = nrows * W;
+        const int lw = ilog2(W), n = nrows << lw;
         for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            const int lr = idx / W, w = idx - lr * W;
+            const int lr = idx >> lw, w = idx & (W - 1);
             const int y = (y_first + lr) & (L - 1);
             dst_plane[(size_t)y * W + w] = src[idx];
         }
     }
 }
 
+// ---- Metropolis update of a strip, device form -----------------------------------------------------------------
+// Same decisions as update_word0()/metropolis_flip_mask() in tile.cuh (the scalar specification is the oracle's
+// orc_metropolis), organised for the SM:
+//   pass 1  every word: neighbour masks, then Philox calls j = 0 and 1 back to back (two independent chains ->
+//           ILP) and 8 lazily-compared bit planes, straight-line, no divergence.  After 8 planes a lane is still
+//           undecided with probability 2^-8, i.e. ~10 % of the words keep a few undecided lanes: those words are
+//           appended to a shared-memory queue (warp-aggregated), decided lanes are written back at once.
+//   pass 2  the queue is consumed densely, one entry per thread, calls j = 2.. until every lane is decided.
+// The per-plane threshold masks (bit k of T4 / T8 replicated over a word) are a 64-entry table in shared memory:
+// broadcast LDS on the otherwise idle LSU pipe instead of shifts on the ALU pipe, which is the binding pipe.
+struct McTable {
+    uint32_t tm[32][2];  // [plane][0: T4 bit, 1: T8 bit] as 0 / 0xFFFFFFFF
+};
+
+__device__ __forceinline__ void mc_compare4(const U4 &r, const McTable *tab, int plane0, uint32_t sel, uint32_t &eq,
+                                            uint32_t &lt) {
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint2 t48 = *reinterpret_cast<const uint2 *>(tab->tm[plane0 + e]);
+        const uint32_t tm = (sel & t48.x) | (~sel & t48.y);  // this lane's threshold bit (A==1 lanes: T4, A==0: T8)
+        lt |= eq & ~rr[e] & tm;                              // U bit 0 where T bit 1, prefix equal: U < T
+        eq &= ~(rr[e] ^ tm);
+    }
+}
+
+__device__ __forceinline__ U4 mc_philox(uint64_t seed, uint32_t word_id, uint32_t replica, uint32_t t_lo, uint32_t c3_base,
+                                        int j) {
+    return philox4x32_10(word_id, replica, t_lo, c3_base | ((uint32_t)j << 20), (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+struct McQueue {
+    int *cnt;        // two counters, used alternately by successive half-sweeps
+    uint32_t *ent;   // [cap][3]: tile word offset, undecided lanes, selector (A==1 lanes)
+    int cap;
+};
+
+__device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
+                                              const McTable *tab, const McQueue &q, int parity, uint64_t seed,
+                                              uint32_t replica, unsigned long long sweep) {
+    const int W = s.W, o = 1 - c;
+    const int n = nrows << lw;
+    const uint32_t t_lo = (uint32_t)sweep;
+    const uint32_t c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
+    uint32_t *plane_c = s.base + c * s.rows * W;
+    const uint32_t *plane_o = s.base + o * s.rows * W;
+    int *cnt = q.cnt + parity;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int idx = base + threadIdx.x;
+        uint32_t eq = 0, sel = 0, off = 0;
+        if (idx < n) {
+            const int lr = lr_lo + (idx >> lw), w = idx & (W - 1);
+            off = (uint32_t)(lr * W + w);
+            const int y = (s.y_first + lr) & (s.L - 1);
+            const uint32_t t = plane_c[off];
+            const uint32_t u = plane_o[off - W], d = plane_o[off + W], n0 = plane_o[off];
+            uint32_t n1;
+            if ((y + c) & 1) n1 = shift_up_index(n0, plane_o[lr * W + ((w + 1) & (W - 1))], s.bits, s.mask);
+            else n1 = shift_down_index(n0, plane_o[lr * W + ((w - 1) & (W - 1))], s.bits, s.mask);
+            const uint32_t a1 = t ^ u ^ anti, a2 = t ^ d ^ anti, a3 = t ^ n0 ^ anti, a4 = t ^ n1 ^ anti;
+            const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
+            const uint32_t ge2 = c12 | c34 | (x12 & x34);
+            sel = (x12 ^ x34) & ~(c12 | c34) & s.mask;         // A == 1
+            eq = (sel | ~(a1 | a2 | a3 | a4)) & s.mask;        // A == 1 or A == 0: lanes that need a random number
+            uint32_t lt = 0;
+            if (eq) {
+                const uint32_t word_id = (uint32_t)((c * s.L + y) * W + w);
+                const U4 r0 = mc_philox(seed, word_id, replica, t_lo, c3_base, 0);
+                const U4 r1 = mc_philox(seed, word_id, replica, t_lo, c3_base, 1);
+                mc_compare4(r0, tab, 0, sel, eq, lt);
+                mc_compare4(r1, tab, 4, sel, eq, lt);
+            }
+            plane_c[off] = t ^ ((ge2 | lt) & s.mask);
+        }
+        // warp-aggregated append of the words that still have undecided lanes
+        const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);
+        if (pend) {
+            const int lane = threadIdx.x & 31;
+            int slot = 0;
+            if (lane == (__ffs(pend) - 1)) slot = atomicAdd(cnt, __popc(pend));
+            slot = __shfl_sync(0xFFFFFFFFu, slot, __ffs(pend) - 1) + __popc(pend & ((1u << lane) - 1u));
+            if (eq != 0u) {
+                if (slot < q.cap) {
+                    q.ent[3 * slot + 0] = off;
+                    q.ent[3 * slot + 1] = eq;
+                    q.ent[3 * slot + 2] = sel;
+                } else {  // queue full (cannot happen for equilibrium-like data; kept for exactness): finish inline
+                    const int lr = (int)off >> lw, w = (int)off & (W - 1);
+                    const int y = (s.y_first + lr) & (s.L - 1);
+                    const uint32_t word_id = (uint32_t)((c * s.L + y) * W + w);
+                    uint32_t lt = 0;
+                    for (int j = 2; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox(seed, word_id, replica, t_lo, c3_base, j), tab, 4 * j, sel, eq, lt);
+                    plane_c[off] ^= lt;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int total = min(*cnt, q.cap);
+    if (threadIdx.x == 0) q.cnt[parity ^ 1] = 0;  // the other counter is idle now: reset it for the next half-sweep
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const uint32_t off = q.ent[3 * e + 0];
+        uint32_t eq = q.ent[3 * e + 1];
+        const uint32_t sel = q.ent[3 * e + 2];
+        const int lr = (int)off >> lw, w = (int)off & (W - 1);
+        const int y = (s.y_first + lr) & (s.L - 1);
+        const uint32_t word_id = (uint32_t)((c * s.L + y) * W + w);
+        uint32_t lt = 0;
+        for (int j = 2; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox(seed, word_id, replica, t_lo, c3_base, j), tab, 4 * j, sel, eq, lt);
+        plane_c[off] ^= lt;
+    }
+    __syncthreads();
+}
+
 template <bool MEASURE>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep0(const SweepArgs a) {
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_sweep0(const SweepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[4];
+    __shared__ __align__(16) McTable tab;
+    __shared__ int q_cnt[2];
     const int r = blockIdx.y, strip = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
     const int rows = a.R + 2 * a.H;
@@ -92,6 +208,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep0(const SweepArgs a) {
     stage_rows(s0_plane(s, 0), src_r, s.y_first, rows, W, L);
     stage_rows(s0_plane(s, 1), src_r + (size_t)L * W, s.y_first, rows, W, L);
     if (MEASURE && threadIdx.x < 4) red[threadIdx.x] = 0;
+    if (threadIdx.x < 2) q_cnt[threadIdx.x] = 0;
+    if (a.nsw > 0) {
+        for (int k = threadIdx.x; k < 64; k += blockDim.x) {  // blockDim may be as small as 32
+            const uint32_t T = (k & 1) ? a.T8[r] : a.T4[r];
+            tab.tm[k >> 1][k & 1] = ((T >> (31 - (k >> 1))) & 1u) ? 0xFFFFFFFFu : 0u;
+        }
+    }
     const unsigned long long t = *a.d_t + a.t_off;
     const uint32_t replica = a.replica_base + (uint32_t)r;
     __syncthreads();
@@ -116,19 +239,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep0(const SweepArgs a) {
     }
 
     if (a.nsw > 0) {
-        McParams p;
-        p.seed = a.seed;
-        p.T4 = a.T4[r];
-        p.T8 = a.T8[r];
-        p.anti = a.anti[r];
-        for (int h = 0; h < 2 * a.nsw; ++h) {
-            const int c = h & 1;
-            const int lr_lo = 1 + h;
-            const int n = (rows - 2 - 2 * h) << lw;
-            for (int idx = threadIdx.x; idx < n; idx += blockDim.x)
-                update_word0(s, c, lr_lo + (idx >> lw), idx & (W - 1), p, replica, t + (unsigned long long)(h >> 1));
-            __syncthreads();
-        }
+        McQueue q;
+        q.cnt = q_cnt;
+        q.ent = smem + 2 * rows * W;
+        q.cap = sweep0_queue_cap(rows * W);
+        const uint32_t anti = a.anti[r];
+        for (int h = 0; h < 2 * a.nsw; ++h)
+            mc_half_sweep(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, h & 1, a.seed, replica,
+                          t + (unsigned long long)(h >> 1));
         uint32_t *dst_r = a.dst + (size_t)r * 2 * L * W;
         unstage_rows(dst_r, s0_plane(s, 0) + a.H * W, y0, a.R, W, L);
         unstage_rows(dst_r + (size_t)L * W, s0_plane(s, 1) + a.H * W, y0, a.R, W, L);
@@ -374,17 +492,23 @@ int g_max_smem = -1;
 
 }  // namespace
 
-size_t sweep0_smem_bytes(int L, int R, int H) { return (size_t)2 * (R + 2 * H) * l0_words(L) * sizeof(uint32_t); }
+size_t sweep0_smem_bytes(int L, int R, int H) {
+    const int words = (R + 2 * H) * l0_words(L);
+    return ((size_t)2 * words + (size_t)3 * sweep0_queue_cap(words)) * sizeof(uint32_t);
+}
 
 int sweep0_max_smem() {
     if (g_max_smem < 0) {
         int dev = 0, v = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        g_max_smem = v;
-        cudaFuncSetAttribute(k_sweep0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
-        cudaFuncSetAttribute(k_sweep0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
-        cudaFuncSetAttribute(k_level, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+        // dynamic limit = opt-in maximum minus the kernels' few bytes of static shared memory
+        const int dyn = v - 1024;
+        cudaError_t e1 = cudaFuncSetAttribute(k_sweep0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaError_t e2 = cudaFuncSetAttribute(k_sweep0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaError_t e3 = cudaFuncSetAttribute(k_level, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        g_max_smem = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) ? dyn : 48 * 1024;
+        (void)cudaGetLastError();  // a refused opt-in only lowers the limit we plan with
     }
     return g_max_smem;
 }

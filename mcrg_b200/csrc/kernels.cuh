@@ -11,6 +11,9 @@ constexpr int MAX_LEVELS = 15;          // L <= 2^15; levels 0..14 at most
 constexpr int NOP = 3;                  // even operators: nn, nnn, plaquette
 constexpr int TAIL_MAX_L = 256;         // blocked lattices up to this size finish inside one CTA's shared memory
 constexpr int SWEEP_THREADS = 256;
+// capacity of the "still undecided after 8 bit planes" queue of a strip with `words` words per colour
+// (expected fill: ~10 % of the words of one colour)
+MCRG_HD int sweep0_queue_cap(int words) { return words / 4 > 64 ? words / 4 : 64; }
 
 // accumulator slots (per replica, per bin), all exact 128-bit integers (lo: uint64, hi: int64)
 constexpr int SLOT_N = 0;                                    // samples
