@@ -287,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"C4: L={L} bit-packed, 5 couplings K in [-0.4897,-0.4320] x {args.replicas_per_k} replicas per GPU, "
                                f"measurement at all {n_lv + 1} levels after every sweep", "L": L, "replicas_per_gpu": n_loc,
                    "samples_per_step": S, "sweeps_per_sample": m, "levels": n_lv + 1, "parallelism": f"replica-sharded x{world}",
-                   "collective": "one int64 all-reduce of 1320 limbs per step",
+                   "collective": f"one int64 all-reduce of {lay.n_slots * 4} limbs per step",
                    "l2": f"state is double-buffered: {2 * n_loc * L * L // 8 >> 20} MiB resident per GPU vs 126 MB L2"
                          + (" (inputs larger than L2)" if 2 * n_loc * L * L // 8 > 126e6 else " (L2-resident by design: 1 bit/spin)"),
                    "cuda_graphs": bool(args.graphs)},

@@ -13,7 +13,7 @@
  *     may be used from distinct threads.
  *   - spins cross the boundary in the reference's layout: int32 +-1, column-major, element (i,j) at j*L+i
  *     (definitions.hpp:16), replicas concatenated.
- *   - L must be a power of two, 4 <= L <= 16384.
+ *   - L must be a power of two, 2 <= L <= 16384.
  *   - all work is enqueued on the context's stream; calls that return host data synchronise it.
  *   - the library is CUDA-only: if no device is present every call fails with MCRG_ERR_CUDA.  There is no CPU
  *     path in the product.
@@ -105,6 +105,8 @@ typedef struct {
     int slot_ss;  /* + lv*9 + b*MCRG_NOP + a           sum S^(lv)_a S^(lv)_b   (Sb_Sb of level lv, mcrg.cpp:89) */
     int slot_sbs; /* + (n-1)*9 + b*MCRG_NOP + a        sum S^(n)_a S^(n-1)_b   (Sb_S, mcrg.cpp:88), flatten order
                                                        of definitions.cpp:9-19 */
+    int slot_sb0; /* + (n-1)*9 + b*MCRG_NOP + a        sum S^(n)_a S^(0)_b     (blocked level against level 0: the two-
+                                                       lattice matching of approx_critical_point, mcrg.cpp:262-263) */
     int dslot_m4; /* sum M^4 (double) */
 } mcrg_acc_layout;
 int mcrg_accumulators_layout(mcrg_acc_layout *out);

@@ -25,7 +25,9 @@ def unpack_slots(acc_vec, n_lv, lay=None):
                    for lv in range(n_lv + 1)], dtype=object)
     SbS = np.array([[[a[lay.slot_sbs + n * NOP * NOP + b * NOP + al] for b in range(NOP)] for al in range(NOP)]
                     for n in range(n_lv)], dtype=object).reshape(n_lv, NOP, NOP)
-    return dict(n=a[lay.slot_n], absM=a[lay.slot_absm], M2=a[lay.slot_m2], S=S, SS=SS, SbS=SbS)
+    Sb0 = np.array([[[a[lay.slot_sb0 + n * NOP * NOP + b * NOP + al] for b in range(NOP)] for al in range(NOP)]
+                    for n in range(n_lv)], dtype=object).reshape(n_lv, NOP, NOP)
+    return dict(n=a[lay.slot_n], absM=a[lay.slot_absm], M2=a[lay.slot_m2], S=S, SS=SS, SbS=SbS, Sb0=Sb0)
 
 
 def _to_float(x, n):

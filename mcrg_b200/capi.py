@@ -21,7 +21,7 @@ class McrgError(RuntimeError):
 
 class AccLayout(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_slots", "n_dslots", "slot_n", "slot_absm", "slot_m2", "slot_s", "slot_ss",
-                                       "slot_sbs", "dslot_m4")]
+                                       "slot_sbs", "slot_sb0", "dslot_m4")]
 
 
 _lib = None

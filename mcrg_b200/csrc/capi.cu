@@ -71,6 +71,7 @@ struct mcrg_ctx {
     int32_t *stage = nullptr;
     size_t stage_ints = 0;
     int last_levels = 0;
+    bool measured = false;
     int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
     std::map<GraphKey, cudaGraphExec_t> graphs;
 };
@@ -198,6 +199,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     launch_tail(ta, c->n_replicas, c->stream);
     if (probe) cudaEventRecord(probe[3], c->stream);
     c->last_levels = n_lv;
+    c->measured = true;
     if (m > 1) enqueue_sweeps(c, m - 1, t_off + 1);
     if (probe) cudaEventRecord(probe[4], c->stream);
 }
@@ -237,7 +239,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
                     mcrg_ctx **out) {
     if (!out) return fail(MCRG_ERR_ARG, "null out pointer");
     *out = nullptr;
-    if (!is_pow2(L) || L < 4 || L > 16384) return fail(MCRG_ERR_ARG, "L=%d must be a power of two in [4, 16384]", L);
+    if (!is_pow2(L) || L < 2 || L > 16384) return fail(MCRG_ERR_ARG, "L=%d must be a power of two in [2, 16384]", L);
     if (n_replicas < 1 || n_replicas > 65535) return fail(MCRG_ERR_ARG, "n_replicas=%d out of range [1, 65535]", n_replicas);
     if (n_bins < 1) return fail(MCRG_ERR_ARG, "n_bins=%d must be >= 1", n_bins);
     int n_dev = 0;
@@ -253,7 +255,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     c->n_bins = n_bins;
     c->seed = seed;
     c->replica_base = replica_base;
-    c->full_levels = ilog2h(L) - 1;
+    c->full_levels = ilog2h(L) - 1;  // mcrg.cpp:43; 0 for the 2x2 lattice
     if (const char *e = getenv("MCRG_STRIP_ROWS")) c->strip_rows = atoi(e);
     if (const char *e = getenv("MCRG_FUSE_SWEEPS")) c->fuse_sweeps = atoi(e) > 0 ? atoi(e) : 1;
     if (const char *e = getenv("MCRG_USE_GRAPHS")) c->use_graphs = atoi(e);
@@ -266,7 +268,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     CK(cudaMalloc(&c->planes[0], plane_words * 4));
     CK(cudaMalloc(&c->planes[1], plane_words * 4));
     size_t off = 0;
-    for (int lv = 1; lv <= c->full_levels; ++lv) {
+    for (int lv = 1; lv <= (c->full_levels > 1 ? c->full_levels : 1); ++lv) {  // level 1 always exists: k_sweep0 writes it
         const int Ln = L >> lv;
         c->level_off[lv] = off;
         size_t words = (size_t)n_replicas * Ln * nat_words(Ln);
@@ -449,7 +451,9 @@ int mcrg_get_spins_i32_colmajor(mcrg_ctx *c, int first, int count, int32_t *host
 int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *c, int replica, int level, int32_t *host) {
     if (!c || !host) return fail(MCRG_ERR_ARG, "null pointer");
     if (replica < 0 || replica >= c->n_replicas) return fail(MCRG_ERR_ARG, "replica %d out of range", replica);
-    if (level < 1 || level > c->last_levels) return fail(MCRG_ERR_STATE, "level %d not produced by the last measurement (levels 1..%d)", level, c->last_levels);
+    // level 1 is written by every measurement (k_sweep0<MEASURE>), deeper levels only up to the requested depth
+    const int have = c->measured ? (c->last_levels > 1 ? c->last_levels : 1) : 0;
+    if (level < 1 || level > have || (c->L >> level) < 1) return fail(MCRG_ERR_STATE, "level %d not produced by the last measurement (levels 1..%d)", level, have);
     CK(cudaSetDevice(c->device));
     const int Ln = c->L >> level;
     const size_t per = (size_t)Ln * Ln;
@@ -617,6 +621,7 @@ int mcrg_accumulators_layout(mcrg_acc_layout *o) {
     o->slot_s = SLOT_S;
     o->slot_ss = SLOT_SS;
     o->slot_sbs = SLOT_SBS;
+    o->slot_sb0 = SLOT_SB0;
     o->dslot_m4 = 0;
     return 0;
 }

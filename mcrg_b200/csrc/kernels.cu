@@ -391,11 +391,16 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
             const int k = slot - SLOT_SS, lv = k / (NOP * NOP), e = k - lv * NOP * NOP, b = e / NOP, al = e - b * NOP;
             live = lv <= a.n_levels;
             if (live) v = (__int128)S_sh[lv * 4 + al] * S_sh[lv * 4 + b];
-        } else {
+        } else if (slot < SLOT_SB0) {
             const int k = slot - SLOT_SBS, n1 = k / (NOP * NOP), e = k - n1 * NOP * NOP, b = e / NOP, al = e - b * NOP;
             const int n = n1 + 1;
             live = n <= a.n_levels;
             if (live) v = (__int128)S_sh[n * 4 + al] * S_sh[(n - 1) * 4 + b];  // flatten: index b*NOP+a holds Sb_a*S_b
+        } else {
+            const int k = slot - SLOT_SB0, n1 = k / (NOP * NOP), e = k - n1 * NOP * NOP, b = e / NOP, al = e - b * NOP;
+            const int n = n1 + 1;
+            live = n <= a.n_levels;
+            if (live) v = (__int128)S_sh[n * 4 + al] * S_sh[b];  // blocked level n against level 0
         }
         if (live) add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], v);
     }

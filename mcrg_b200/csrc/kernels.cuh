@@ -22,7 +22,9 @@ constexpr int SLOT_M2 = 2;                                   // sum M^2
 constexpr int SLOT_S = 3;                                    // + lv*NOP + op          sum S^(lv)_op
 constexpr int SLOT_SS = SLOT_S + NOP * (MAX_LEVELS + 1);     // + lv*9 + b*3 + a        sum S^(lv)_a S^(lv)_b
 constexpr int SLOT_SBS = SLOT_SS + NOP * NOP * (MAX_LEVELS + 1);  // + (n-1)*9 + b*3 + a  sum S^(n)_a S^(n-1)_b
-constexpr int N_SLOTS = SLOT_SBS + NOP * NOP * MAX_LEVELS;
+constexpr int SLOT_SB0 = SLOT_SBS + NOP * NOP * MAX_LEVELS;       // + (n-1)*9 + b*3 + a  sum S^(n)_a S^(0)_b  (two-lattice
+                                                                  //   matching needs S(blocked) x S(level 0), mcrg.cpp:262-263)
+constexpr int N_SLOTS = SLOT_SB0 + NOP * NOP * MAX_LEVELS;
 constexpr int N_DSLOTS = 1;  // double slots: sum M^4
 
 struct SweepArgs {

@@ -1,0 +1,508 @@
+// Implementation of the drop-in classes (mcrg_dropin.hpp) over the C ABI of libmcrg_b200.so.
+// Host code only orchestrates: every lattice operation of the hot path is a call into the device library, and a
+// failing call throws — there is no CPU implementation of the path here.
+#include "mcrg_dropin.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <stdexcept>
+
+#include "../../../include/mcrg_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// definitions.cpp
+// ---------------------------------------------------------------------------------------------------------
+
+std::random_device rd;
+std::mt19937_64 rng(rd());  // definitions.cpp:3-4: non-deterministic seed, as in the reference
+std::uniform_int_distribution<int> binary(0, 1);
+std::uniform_real_distribution<double> unif(0.0, 1.0);
+std::normal_distribution<double> norm(0.0, 1.0);
+
+vec flatten(mat M) {
+    // definitions.cpp:9-19: columns laid end to end
+    const int n = (int)M.cols();
+    vec v(n * n);
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) v(j * n + i) = M(i, j);
+    return v;
+}
+
+mat unflatten(vec v) {
+    // definitions.cpp:21-31
+    const int n = (int)std::floor(std::sqrt((double)v.size()));
+    mat M(n, n);
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) M(i, j) = v(j * n + i);
+    return M;
+}
+
+void display_spin_up() { printf("\033[34m%2s\033[0m", "O"); }
+void display_spin_down() { printf("\033[37m%2s\033[0m", "X"); }
+
+bool write_iter(int i) {
+    // definitions.cpp:44-68: every iteration below 10, then every 10^k below 10^(k+1), then every 10^5
+    int step = 1;
+    for (int bound = 10; bound <= 100000; bound *= 10) {
+        if (i < bound) return i % step == 0;
+        step = bound;
+    }
+    return i % 100000 == 0;
+}
+
+std::string get_rounded_str(double num, int precision) {
+    std::stringstream ss;
+    ss << std::setprecision(precision) << num;
+    return ss.str();
+}
+
+int split_samples(int rank, int n_processes, int n_samples) {
+    // definitions.cpp:79-87 (including its behaviour when n_samples < n_processes^2: rank 0 takes the remainder)
+    int n_loc = (int)std::ceil((double)n_samples / (double)n_processes);
+    if (rank == 0) n_loc = n_samples - (n_processes - 1) * n_loc;
+    return n_loc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device plumbing
+// ---------------------------------------------------------------------------------------------------------
+
+namespace mcrg_b200 {
+
+static void ck(int rc, const char *what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + mcrg_last_error());
+}
+
+static long env_long(const char *name, long dflt) {
+    const char *e = std::getenv(name);
+    return (e && *e) ? std::atol(e) : dflt;
+}
+
+Settings &settings() {
+    static Settings s = {(int)env_long("MCRG_REPLICAS", 1024), (int)env_long("MCRG_SWEEPS_PER_UPDATE", 1),
+                         (int)env_long("MCRG_DEVICE", 0), (std::uint64_t)env_long("MCRG_SEED", 12345),
+                         (int)env_long("MCRG_QUIET", 0)};
+    if (s.replicas < 1) s.replicas = 1;
+    if (s.sweeps_per_update < 1) s.sweeps_per_update = 1;
+    return s;
+}
+
+struct DeviceBatch {
+    mcrg_ctx *ctx = nullptr;
+    int L = 0, replicas = 0;
+    DeviceBatch(int L_, int replicas_, std::uint32_t replica_base) : L(L_), replicas(replicas_) {
+        ck(mcrg_ctx_create(settings().device, L, replicas, settings().seed, replica_base, 1, &ctx), "mcrg_ctx_create");
+    }
+    ~DeviceBatch() { mcrg_ctx_destroy(ctx); }
+    DeviceBatch(const DeviceBatch &) = delete;
+    DeviceBatch &operator=(const DeviceBatch &) = delete;
+};
+
+// Lattice objects get Philox replica ids above the range the drivers use for their batches
+static std::atomic<std::uint32_t> g_next_lattice_id{0x40000000u};
+// successive driver calls must not reuse Philox streams: each call takes a fresh block of replica ids
+static std::atomic<std::uint32_t> g_next_batch_base{0};
+
+static std::uint32_t take_batch_base(int replicas) { return g_next_batch_base.fetch_add((std::uint32_t)replicas); }
+
+// exact 128-bit accumulator -> long double (64-bit mantissa: ample for covariances of ~1e-3 relative size)
+static long double to_ld(std::int64_t hi, std::uint64_t lo) { return (long double)hi * 18446744073709551616.0L + (long double)lo; }
+
+struct Totals {
+    std::vector<long double> v;  // [n_slots], summed over replicas
+    std::vector<std::vector<long double>> per_replica;
+};
+
+static Totals fetch_totals(DeviceBatch &b) {
+    mcrg_acc_layout lay;
+    ck(mcrg_accumulators_layout(&lay), "mcrg_accumulators_layout");
+    const size_t n = (size_t)b.replicas * lay.n_slots;
+    std::vector<std::int64_t> hi(n);
+    std::vector<std::uint64_t> lo(n);
+    ck(mcrg_accumulators_get(b.ctx, hi.data(), lo.data(), nullptr), "mcrg_accumulators_get");
+    Totals t;
+    t.v.assign(lay.n_slots, 0.0L);
+    t.per_replica.assign(b.replicas, std::vector<long double>(lay.n_slots));
+    for (int r = 0; r < b.replicas; ++r)
+        for (int s = 0; s < lay.n_slots; ++s) {
+            const long double x = to_ld(hi[(size_t)r * lay.n_slots + s], lo[(size_t)r * lay.n_slots + s]);
+            t.per_replica[r][s] = x;
+            t.v[s] += x;
+        }
+    return t;
+}
+
+// mcrg.cpp:111-131 for the reference's operator pair (NN, NNN): A = <SbSb>-<Sb><Sb>^T, B = <SbS>-<Sb><S>^T,
+// T = A^-1 B, lambda = larger real part of T's eigenvalues
+static std::vector<double> lambdas_from(const std::vector<long double> &v, int n_lv) {
+    mcrg_acc_layout lay;
+    mcrg_accumulators_layout(&lay);
+    const long double n = v[lay.slot_n];
+    std::vector<double> out(n_lv, NAN);
+    for (int lv = 0; lv < n_lv; ++lv) {
+        long double A[2][2], B[2][2];
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                const long double sb_a = v[lay.slot_s + (lv + 1) * MCRG_NOP + a] / n, sb_b = v[lay.slot_s + (lv + 1) * MCRG_NOP + b] / n;
+                const long double s_b = v[lay.slot_s + lv * MCRG_NOP + b] / n;
+                A[a][b] = v[lay.slot_ss + (lv + 1) * 9 + b * MCRG_NOP + a] / n - sb_a * sb_b;
+                B[a][b] = v[lay.slot_sbs + lv * 9 + b * MCRG_NOP + a] / n - sb_a * s_b;
+            }
+        const long double det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+        if (det == 0.0L) continue;
+        const long double Ai[2][2] = {{A[1][1] / det, -A[0][1] / det}, {-A[1][0] / det, A[0][0] / det}};
+        long double T[2][2];
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) T[i][j] = Ai[i][0] * B[0][j] + Ai[i][1] * B[1][j];
+        const long double tr = T[0][0] + T[1][1], dt = T[0][0] * T[1][1] - T[0][1] * T[1][0];
+        const long double disc = tr * tr / 4 - dt;
+        out[lv] = (double)(disc < 0 ? tr / 2 : tr / 2 + std::sqrt(disc));
+    }
+    return out;
+}
+
+}  // namespace mcrg_b200
+
+using mcrg_b200::ck;
+using mcrg_b200::DeviceBatch;
+using mcrg_b200::settings;
+
+// ---------------------------------------------------------------------------------------------------------
+// Lattice  (lattice.cpp)
+// ---------------------------------------------------------------------------------------------------------
+
+Lattice::Lattice(int N) {
+    MPI_Comm_size(MPI_COMM_WORLD, &n_processes_);
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank_);
+    a_ = 1;
+    N_ = N;
+    n_spins_ = N * N;
+    pick_site_ = std::uniform_int_distribution<int>(0, n_spins_ - 1);
+    // hot start, lattice.cpp:33-41: i.i.d. fair spins from the host generator, i outer / j inner
+    spins_.resize(N, N);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) spins_(i, j) = rand_spin();
+}
+
+Lattice::Lattice(int a, imat spins) {
+    MPI_Comm_size(MPI_COMM_WORLD, &n_processes_);
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank_);
+    spins_ = spins;
+    a_ = a;
+    N_ = (int)spins_.rows();
+    n_spins_ = N_ * N_;
+    pick_site_ = std::uniform_int_distribution<int>(0, n_spins_ - 1);
+}
+
+Lattice::~Lattice() {}
+
+std::shared_ptr<DeviceBatch> Lattice::device_batch() {
+    if (!dev_) dev_ = std::make_shared<DeviceBatch>(N_, 1, mcrg_b200::g_next_lattice_id.fetch_add(1));
+    return dev_;
+}
+
+void Lattice::display_spins() {
+    if (rank_ != 0) return;
+    for (int i = 0; i < N_; ++i) {
+        for (int j = 0; j < N_; ++j) (spins_(i, j) == 1) ? display_spin_up() : display_spin_down();
+        printf("\n");
+    }
+    printf("(Lattice spacing a = %i)\n\n", a_);
+}
+
+void Lattice::write_spins(FILE *fptr) {
+    if (rank_ != 0) return;
+    fprintf(fptr, "\n");
+    for (int i = 0; i < N_; ++i) {
+        fprintf(fptr, "# ");
+        for (int j = 0; j < N_; ++j) fprintf(fptr, "%i, ", spins_(i, j));
+        fprintf(fptr, "\n");
+    }
+}
+
+int Lattice::choose_random_spin() { return pick_site_(rng); }
+
+static void observe(Lattice &lat, std::int64_t out[4]) {
+    auto b = lat.device_batch();
+    ck(mcrg_set_spins_i32_colmajor(b->ctx, 0, 1, lat.spins_.data()), "mcrg_set_spins_i32_colmajor");
+    ck(mcrg_observables(b->ctx, &out[0], &out[1], &out[2], &out[3]), "mcrg_observables");
+}
+
+double Lattice::calc_nearest_neighbor_interaction() {
+    std::int64_t o[4];
+    observe(*this, o);
+    return (double)o[0];
+}
+
+vec2D Lattice::calc_interactions() {
+    std::int64_t o[4];
+    observe(*this, o);
+    vec2D S;
+    S(0) = (double)o[0];
+    S(1) = (double)o[1];
+    return S;
+}
+
+double Lattice::calc_plaquette_interaction() {
+    std::int64_t o[4];
+    observe(*this, o);
+    return (double)o[2];
+}
+
+long long Lattice::sum_spins() {
+    std::int64_t o[4];
+    observe(*this, o);
+    return (long long)o[3];
+}
+
+static int wrap(int x, int N) { return ((x % N) + N) % N; }
+
+imat Lattice::nearest_neighbors(int i, int j) {
+    // lattice.cpp:124-136: rows = (+i, -i, +j, -j), columns = (row index, column index)
+    imat nn(4, 2);
+    nn(0, 0) = wrap(i + 1, N_); nn(0, 1) = j;
+    nn(1, 0) = wrap(i - 1, N_); nn(1, 1) = j;
+    nn(2, 0) = i;               nn(2, 1) = wrap(j + 1, N_);
+    nn(3, 0) = i;               nn(3, 1) = wrap(j - 1, N_);
+    return nn;
+}
+
+imat Lattice::next_nearest_neighbors(int i, int j) {
+    // lattice.cpp:139-151
+    imat nnn(4, 2);
+    nnn(0, 0) = wrap(i + 1, N_); nnn(0, 1) = wrap(j + 1, N_);
+    nnn(1, 0) = wrap(i - 1, N_); nnn(1, 1) = wrap(j + 1, N_);
+    nnn(2, 0) = wrap(i + 1, N_); nnn(2, 1) = wrap(j - 1, N_);
+    nnn(3, 0) = wrap(i - 1, N_); nnn(3, 1) = wrap(j - 1, N_);
+    return nnn;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// IsingModel  (ising.cpp)
+// ---------------------------------------------------------------------------------------------------------
+
+IsingModel::IsingModel(double K) {
+    MPI_Comm_size(MPI_COMM_WORLD, &n_processes_);
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank_);
+    K_ = K;
+    fptr_ = NULL;
+}
+
+static void device_sweeps(Lattice &lat, double K, int n_updates) {
+    auto b = lat.device_batch();
+    ck(mcrg_set_couplings(b->ctx, &K, 1), "mcrg_set_couplings");
+    ck(mcrg_set_spins_i32_colmajor(b->ctx, 0, 1, lat.spins_.data()), "mcrg_set_spins_i32_colmajor");
+    ck(mcrg_sweep(b->ctx, n_updates * settings().sweeps_per_update), "mcrg_sweep");
+    ck(mcrg_get_spins_i32_colmajor(b->ctx, 0, 1, lat.spins_.data()), "mcrg_get_spins_i32_colmajor");
+}
+
+void IsingModel::sample_new_configuration(std::shared_ptr<Lattice> pLattice) { device_sweeps(*pLattice, K_, 1); }
+
+double IsingModel::calc_energy(std::shared_ptr<Lattice> pLattice) {
+    // ising.cpp:158-173 is K*S_nn/N^2 accumulated term by term; the integer S_nn is exact here
+    return K_ * pLattice->calc_nearest_neighbor_interaction() / (pLattice->N_ * pLattice->N_);
+}
+
+double IsingModel::calc_magnetization(std::shared_ptr<Lattice> pLattice) {
+    // ising.cpp:176-179: INTEGER division of the spin sum by N*N (so -1, 0 or +1)
+    const int sum = (int)pLattice->sum_spins();
+    return (double)(sum / (pLattice->N_ * pLattice->N_));
+}
+
+void IsingModel::equilibrate(std::shared_ptr<Lattice> pLattice, int n_samples_eq, bool write) {
+    if (!write) {
+        device_sweeps(*pLattice, K_, n_samples_eq);
+        return;
+    }
+    // ising.cpp:22-74: thermodynamics log at log-spaced iterations, same file name and row format; the averages
+    // are over processes (one here), and E (already per spin) is divided by n_spins_ once more when printed,
+    // exactly as the reference does (ising.cpp:72)
+    if (rank_ == 0) {
+        const std::string filename = "equilibrate_N_" + std::to_string(pLattice->N_) + "_K_" + get_rounded_str(K_, 7) + ".txt";
+        fptr_ = fopen(filename.c_str(), "w");
+        if (!fptr_) throw std::runtime_error("cannot open " + filename);
+        fprintf(fptr_, "# Nearest neighbor coupling K = %lf\n", K_);
+        fprintf(fptr_, "# Temperature T = %lf\n", -1 / K_);
+        fprintf(fptr_, "# Number of lattice sites = %i\n", pLattice->N_ * pLattice->N_);
+        fprintf(fptr_, "# Lattice spacing = %i\n", pLattice->a_);
+        fprintf(fptr_, "# Using %i parallel processes\n", n_processes_);
+        fprintf(fptr_, "# %s, %s, %s, %s, %s, %s, %s\n", "Iteration", "Avg E/spin", "Stddev E/spin", "Heat Capacity",
+                "Avg |M|/spin", "Stddev |M|/spin", "Susceptibility");
+    }
+    for (int n = 1; n <= n_samples_eq; ++n) {
+        sample_new_configuration(pLattice);
+        if (write_iter(n) && rank_ == 0) {
+            const double E = calc_energy(pLattice), M = std::fabs(calc_magnetization(pLattice));
+            const double E_avg = E / n_processes_, M_avg = M / n_processes_;
+            const double E2_avg = E * E / n_processes_, M2_avg = M * M / n_processes_;
+            double E_sigma = E2_avg - E_avg * E_avg, M_sigma = M2_avg - M_avg * M_avg;
+            const double C = E_sigma * K_ * K_, Chi = -M_sigma * K_;
+            E_sigma = std::sqrt(E_sigma);
+            M_sigma = std::sqrt(M_sigma);
+            fprintf(fptr_, "%i, %10.7e, %10.7e, %10.7e, %10.7e, %10.7e, %10.7e\n", n, E_avg / pLattice->n_spins_,
+                    E_sigma / pLattice->n_spins_, C, M_avg / pLattice->n_spins_, M_sigma / pLattice->n_spins_, Chi);
+        }
+    }
+    if (rank_ == 0) {
+        pLattice->write_spins(fptr_);
+        fclose(fptr_);
+        fptr_ = NULL;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MonteCarloRenormalizationGroup  (mcrg.cpp)
+// ---------------------------------------------------------------------------------------------------------
+
+MonteCarloRenormalizationGroup::MonteCarloRenormalizationGroup(int b) {
+    b_ = b;
+    fptr_ = NULL;
+    iter_ = 0;
+    rank_ = 0;
+    n_processes_ = settings().replicas;  // independent chains on the device stand in for the reference's MPI ranks
+    if (b != 2) throw std::invalid_argument("mcrg_b200: only the b = 2 block-spin transformation is implemented on the device");
+    if (!settings().quiet) {
+        printf("\n=============================================\n");
+        printf("==========       MONTE CARLO       ==========\n");
+        printf("==========  RENORMALIZATION GROUP  ==========\n");
+        printf("=============================================\n\n");
+        printf("* Using %i parallel process(es)\n", n_processes_);
+        printf("* Scaling factor b = %i\n", b_);
+    }
+}
+
+void MonteCarloRenormalizationGroup::calc_critical_exponent(int n_samples_eq, int n_samples, int N, double K) {
+    const std::string filename = "critical_exponent_N_" + std::to_string(N) + "_K_" + get_rounded_str(K, 7) + ".txt";
+    if (!settings().quiet) printf("* Calculating critical exponent at K = %lf\n\n", K);
+    fptr_ = fopen(filename.c_str(), "w");
+    if (!fptr_) throw std::runtime_error("cannot open " + filename);
+    fprintf(fptr_, "# Number of parallel processes = %i\n", n_processes_);
+    fprintf(fptr_, "# Number of equilibration samples = %i\n", n_samples_eq);
+    fprintf(fptr_, "# Number of samples = %i\n", n_samples);
+    fprintf(fptr_, "# %23s  %25s  %25s\n", "Blocking Level n", "Largest Eigenvalue", "Critical Exponent nu");
+
+    const int R = n_processes_;
+    const int per_replica = (n_samples + R - 1) / R;  // every chain takes ceil(n/R): SURVEY 7.0-9, no negative remainder
+    const int n_lv = mcrg_levels_full(N);             // floor(log N / log b) - 1, mcrg.cpp:43
+    const int spu = settings().sweeps_per_update;
+    DeviceBatch batch(N, R, mcrg_b200::take_batch_base(R));
+    ck(mcrg_set_couplings(batch.ctx, &K, 1), "mcrg_set_couplings");
+    ck(mcrg_init_hot(batch.ctx), "mcrg_init_hot");                        // Lattice(N), mcrg.cpp:49
+    ck(mcrg_sweep(batch.ctx, n_samples_eq * spu), "mcrg_sweep");            // equilibrate, mcrg.cpp:50
+    if (!settings().quiet) printf("Sampling %i configurations...\n", n_samples);
+    ck(mcrg_run(batch.ctx, per_replica, spu, n_lv, 0), "mcrg_run");         // the sample loop, mcrg.cpp:72-98
+    mcrg_b200::Totals tot = mcrg_b200::fetch_totals(batch);                 // the all-reduce, mcrg.cpp:101-103
+
+    lambdas_ = mcrg_b200::lambdas_from(tot.v, n_lv);
+    nus_.assign(n_lv, NAN);
+    lambda_errors_.assign(n_lv, NAN);
+    // jackknife over chains (the reference prints point estimates only)
+    if (R >= 8) {
+        const int groups = std::min(R, 32);
+        std::vector<std::vector<double>> loo;
+        for (int g = 0; g < groups; ++g) {
+            std::vector<long double> v = tot.v;
+            for (int r = g; r < R; r += groups)
+                for (size_t s = 0; s < v.size(); ++s) v[s] -= tot.per_replica[r][s];
+            loo.push_back(mcrg_b200::lambdas_from(v, n_lv));
+        }
+        for (int lv = 0; lv < n_lv; ++lv) {
+            double mean = 0, var = 0;
+            for (auto &l : loo) mean += l[lv];
+            mean /= groups;
+            for (auto &l : loo) var += (l[lv] - mean) * (l[lv] - mean);
+            lambda_errors_[lv] = std::sqrt(var * (groups - 1) / groups);
+        }
+    }
+    double nu = 0.0;
+    for (int n = 0; n < n_lv; ++n) {
+        nu = std::log((double)b_) / std::log(lambdas_[n]);  // mcrg.cpp:131
+        nus_[n] = nu;
+        if (!settings().quiet) printf("n = %i: lambda = %lf, nu = %lf\n", n, lambdas_[n], nu);
+        fprintf(fptr_, "%25i, %25.10lf, %25.10lf\n", n, lambdas_[n], nu);
+    }
+    if (!settings().quiet) printf("\n* Critical exponent: nu = %lf\n", nu);
+    fclose(fptr_);
+    fptr_ = NULL;
+}
+
+double MonteCarloRenormalizationGroup::locate_critical_point(int n_iterations, int n_samples_eq, int n_samples, int L, double K0) {
+    if (!settings().quiet) printf("* Locating critical point starting from K0 = %lf\n", K0);
+    const std::string filename = "critical_point_L_" + std::to_string(L) + "_K_" + get_rounded_str(K0, 7) + ".txt";
+    fptr_ = fopen(filename.c_str(), "w");
+    if (!fptr_) throw std::runtime_error("cannot open " + filename);
+    fprintf(fptr_, "# Number of parallel processes = %i\n", n_processes_);
+    fprintf(fptr_, "# Number of equilibration samples = %i\n", n_samples_eq);
+    fprintf(fptr_, "# Number of samples = %i\n", n_samples);
+    fprintf(fptr_, "# %23s  %25s  %25s  %25s\n", "Iteration", "Blocking Level n", "Starting K", "Approximate Kc");
+    double K = K0;
+    for (iter_ = 1; iter_ <= n_iterations; ++iter_) {
+        if (!settings().quiet) printf("\nIteration %i:\n", iter_);
+        K = approx_critical_point(n_samples_eq, n_samples, L, K);
+    }
+    if (!settings().quiet) {
+        printf("\n* Critical point: Kc = %lf\n", K);
+        printf("* Critical temperature: Tc = %lf\n", -1.0 / K);
+    }
+    fclose(fptr_);
+    fptr_ = NULL;
+    return K;
+}
+
+double MonteCarloRenormalizationGroup::approx_critical_point(int n_samples_eq, int n_samples, int L, double K) {
+    // mcrg.cpp:191-310, Swendsen's two-lattice matching with the NN operator: lattice L blocked n+1 times is
+    // compared with lattice L/b blocked n times.  Both batches run on the device; the six reductions of
+    // mcrg.cpp:275-280 are reads of the accumulators.
+    const int R = n_processes_;
+    const int per_replica = (n_samples + R - 1) / R;
+    const int nT = mcrg_levels_full(L);  // mcrg.cpp:196
+    const int spu = settings().sweeps_per_update;
+    const int S = L / b_;
+    mcrg_acc_layout lay;
+    ck(mcrg_accumulators_layout(&lay), "mcrg_accumulators_layout");
+
+    DeviceBatch big(L, R, mcrg_b200::take_batch_base(R)), small(S, R, mcrg_b200::take_batch_base(R));
+    for (DeviceBatch *b : {&big, &small}) {
+        ck(mcrg_set_couplings(b->ctx, &K, 1), "mcrg_set_couplings");
+        ck(mcrg_init_hot(b->ctx), "mcrg_init_hot");
+        ck(mcrg_sweep(b->ctx, n_samples_eq * spu), "mcrg_sweep");
+    }
+    if (!settings().quiet) printf("Sampling %i configurations each...\n", n_samples);
+    ck(mcrg_run(big.ctx, per_replica, spu, nT, 0), "mcrg_run");                       // levels 0..nT of L
+    ck(mcrg_run(small.ctx, per_replica, spu, nT > 0 ? nT - 1 : 0, 0), "mcrg_run");    // levels 0..nT-1 of L/b
+    const std::vector<long double> vL = mcrg_b200::fetch_totals(big).v, vS = mcrg_b200::fetch_totals(small).v;
+    const long double n = vL[lay.slot_n];
+
+    const long double SL_avg = vL[lay.slot_s + 0] / n, SS_avg = vS[lay.slot_s + 0] / n;
+    double Kc = 0;
+    for (int k = 0; k < nT; ++k) {
+        // SLb(k): NN sum of L blocked k+1 times; SSb(k): NN sum of L/b blocked k times (mcrg.cpp:253-263)
+        const long double SLb = vL[lay.slot_s + (k + 1) * MCRG_NOP + 0] / n;
+        const long double SSb = vS[lay.slot_s + k * MCRG_NOP + 0] / n;
+        const long double SLb_SL = vL[lay.slot_sb0 + k * 9 + 0] / n;
+        const long double SSb_SS = (k == 0 ? vS[lay.slot_ss + 0] : vS[lay.slot_sb0 + (k - 1) * 9 + 0]) / n;
+        const long double dSL_dK = SLb_SL - SLb * SL_avg;  // mcrg.cpp:295
+        const long double dSS_dK = SSb_SS - SSb * SS_avg;  // mcrg.cpp:296
+        const long double dK = (SLb - SSb) / (dSL_dK - dSS_dK);
+        Kc = K + (double)dK;
+        if (!settings().quiet) printf("n = %i: Kc = %lf\n", k, Kc);
+        fprintf(fptr_, "%25i, %25i, %25.10lf, %25.10lf\n", iter_, k, K, Kc);
+        fflush(fptr_);
+    }
+    return Kc;
+}
+
+std::shared_ptr<Lattice> MonteCarloRenormalizationGroup::block_spin_transformation(std::shared_ptr<Lattice> pLattice) {
+    // mcrg.cpp:314-348 for b = 2: majority rule on the device, ties by Philox (keyed by the lattice's id and a
+    // per-call counter so that repeated calls draw fresh coins)
+    auto b = pLattice->device_batch();
+    static std::atomic<std::uint64_t> calls{0};
+    ck(mcrg_set_spins_i32_colmajor(b->ctx, 0, 1, pLattice->spins_.data()), "mcrg_set_spins_i32_colmajor");
+    ck(mcrg_set_sweep_counter(b->ctx, (1ull << 40) + calls.fetch_add(1)), "mcrg_set_sweep_counter");
+    ck(mcrg_measure(b->ctx, 1, nullptr, nullptr), "mcrg_measure");
+    const int Nb = pLattice->N_ / b_;
+    imat block_spins(Nb, Nb);
+    ck(mcrg_get_level_spins_i32_colmajor(b->ctx, 0, 1, block_spins.data()), "mcrg_get_level_spins_i32_colmajor");
+    return std::shared_ptr<Lattice>(new Lattice(pLattice->a_ * b_, block_spins));
+}

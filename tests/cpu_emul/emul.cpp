@@ -180,7 +180,7 @@ Emu make(int L, uint64_t seed, uint32_t replica, uint32_t T4, uint32_t T8, uint3
     e.planes[0].assign((size_t)2 * L * e.W, 0u);
     e.planes[1].assign((size_t)2 * L * e.W, 0u);
     e.levels.resize(MAX_LEVELS + 1);
-    for (int lv = 1; (L >> lv) >= 2; ++lv) e.levels[lv].assign((size_t)(L >> lv) * nat_words(L >> lv), 0u);
+    for (int lv = 1; (L >> lv) >= 2 || lv == 1; ++lv) e.levels[lv].assign((size_t)(L >> lv) * nat_words(L >> lv), 0u);  // level 1 always: sweep0 writes it
     std::memset(e.cnt, 0, sizeof e.cnt);
     e.mc.seed = seed;
     e.mc.T4 = T4;

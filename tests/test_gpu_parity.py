@@ -32,7 +32,7 @@ def oracle_hot(L, seed, replica):
 # transport and initial conditions
 # ---------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("L,R", [(4, 3), (8, 5), (16, 2), (32, 3), (64, 4), (128, 3), (256, 2), (1024, 2)])
+@pytest.mark.parametrize("L,R", [(2, 4), (4, 3), (8, 5), (16, 2), (32, 3), (64, 4), (128, 3), (256, 2), (1024, 2)])
 def test_pack_unpack_roundtrip(mc, L, R):
     spins = np.stack([_libs.random_lattice(L, 10 + r) for r in range(R)])
     with mc.Context(L, R) as ctx:
@@ -45,7 +45,7 @@ def test_pack_unpack_roundtrip(mc, L, R):
         assert np.array_equal(got[: R - 1], spins[: R - 1])
 
 
-@pytest.mark.parametrize("L", [4, 8, 32, 64, 128, 512])
+@pytest.mark.parametrize("L", [2, 4, 8, 32, 64, 128, 512])
 def test_hot_start_matches_oracle(mc, L):
     with mc.Context(L, 3, seed=777, replica_base=5) as ctx:
         ctx.init_hot()
@@ -57,7 +57,7 @@ def test_hot_start_matches_oracle(mc, L):
 
 
 def test_bad_arguments_are_reported(mc):
-    for L in (0, 3, 6, 100, 32768):
+    for L in (0, 1, 3, 6, 100, 32768):
         with pytest.raises(mc.McrgError):
             mc.Context(L, 1)
     with pytest.raises(mc.McrgError):
@@ -89,7 +89,7 @@ def lattice_cases(L):
     return cases
 
 
-@pytest.mark.parametrize("L", [4, 8, 16, 32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("L", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024])
 def test_observables_match_oracle(mc, L):
     o = _libs.oracle()
     cases = lattice_cases(L)
@@ -144,13 +144,12 @@ def test_golden_reference_vectors(mc):
         N = int(str(key).split("_")[0][1:])
         by_N.setdefault(N, []).append(str(key))
     for N, keys in by_N.items():
-        if N < 4:
-            continue  # contexts start at L = 4; the 2x2 lattice is reached as the last pyramid level
         spins = np.stack([np.where(np.unpackbits(g[k + "_bits"])[: N * N].reshape(N, N) > 0, 1, -1) for k in keys]).astype(np.int32)
         with mc.Context(N, len(keys), seed=1) as ctx:
             ctx.set_spins(spins)
             obs = ctx.observables()
-            ctx.measure(max_levels=1)
+            if N >= 4:
+                ctx.measure(max_levels=1)
             for r, k in enumerate(keys):
                 ref = g[k + "_ref"]
                 assert obs["Snn"][r] == ref[0] and obs["Snnn"][r] == ref[1] and obs["Snn"][r] == ref[2], k
@@ -159,6 +158,8 @@ def test_golden_reference_vectors(mc):
                 assert abs(KC * obs["Snn"][r] / (N * N) - ref[3]) <= 1e-12 * max(1.0, abs(ref[3])), k
                 # IsingModel::calc_magnetization: integer division (ising.cpp:178)
                 assert float(int(obs["M"][r] / (N * N))) == ref[4], k
+                if N < 4:
+                    continue
                 want_blk = np.where(np.unpackbits(g[k + "_block_bits"])[: (N // 2) ** 2].reshape(N // 2, N // 2) > 0, 1, -1)
                 got_blk = ctx.get_level_spins(r, 1)
                 nontie = spins[r].reshape(N // 2, 2, N // 2, 2).sum(axis=(1, 3)) != 0
@@ -186,7 +187,7 @@ def test_tie_coins_are_fair_and_keyed(mc):
 # Metropolis trajectories   (bit-exact against the scalar specification with the same Philox keys)
 # ---------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("L,strip,fuse,n_sweeps", [(4, 0, 1, 3), (8, 2, 1, 4), (16, 0, 2, 5), (32, 8, 1, 3), (64, 0, 1, 4),
+@pytest.mark.parametrize("L,strip,fuse,n_sweeps", [(2, 0, 1, 5), (2, 2, 2, 4), (4, 0, 1, 3), (8, 2, 1, 4), (16, 0, 2, 5), (32, 8, 1, 3), (64, 0, 1, 4),
                                                    (64, 16, 3, 7), (128, 0, 2, 3), (256, 32, 1, 2), (512, 0, 1, 2),
                                                    (1024, 16, 2, 2)])
 def test_sweeps_match_scalar_metropolis(mc, L, strip, fuse, n_sweeps):
@@ -290,6 +291,7 @@ def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start):
         n_lv = max_levels
     S_sum = np.zeros((n_lv + 1) * 3, np.int64)
     SS = [[0] * 9 for _ in range(n_lv + 1)]
+    SB0 = [[0] * 9 for _ in range(n_lv)]
     hi1 = np.zeros(n_lv * 9, np.int64); lo1 = np.zeros(n_lv * 9, np.uint64)
     hi2 = np.zeros(n_lv * 9, np.int64); lo2 = np.zeros(n_lv * 9, np.uint64)
     absM = M2 = 0
@@ -303,13 +305,15 @@ def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start):
             for b in range(3):
                 for a in range(3):
                     SS[lv][b * 3 + a] += int(S3[lv, a]) * int(S3[lv, b])
+                    if lv >= 1:
+                        SB0[lv - 1][b * 3 + a] += int(S3[lv, a]) * int(S3[0, b])
         M = int(S4[0, 3])
         absM += abs(M); M2 += M * M; M4 += float(M) ** 4
         o.orc_metropolis(L, s, K, seed, replica, t, m)
         t += m
     SbS = [int(h) * (1 << 64) + int(l) for h, l in zip(hi1, lo1)]
     SbSb = [int(h) * (1 << 64) + int(l) for h, l in zip(hi2, lo2)]
-    return dict(n=n_samples, absM=absM, M2=M2, M4=M4, S=S_sum, SS=SS, SbS=SbS, SbSb=SbSb, final=s, n_lv=n_lv)
+    return dict(n=n_samples, absM=absM, M2=M2, M4=M4, S=S_sum, SS=SS, SbS=SbS, SbSb=SbSb, SB0=SB0, final=s, n_lv=n_lv)
 
 
 @pytest.mark.parametrize("L,n_samples,m,max_levels,graphs", [(8, 5, 1, -1, 0), (16, 20, 2, -1, 1), (64, 37, 1, -1, 1),
@@ -355,6 +359,7 @@ def test_run_accumulators_match_oracle(mc, L, n_samples, m, max_levels, graphs):
             for e in range(9):
                 assert a[lay.slot_sbs + n * 9 + e] == want["SbS"][n * 9 + e], (r, n, e)
                 assert a[lay.slot_ss + (n + 1) * 9 + e] == want["SbSb"][n * 9 + e], (r, n, e)  # Sb_Sb == SS of level n+1
+                assert a[lay.slot_sb0 + n * 9 + e] == want["SB0"][n][e], (r, n, e)
         # slots of levels that do not exist stay zero
         for lv in range(n_lv + 1, mc.capi.MAX_LEVELS + 1):
             assert all(a[lay.slot_s + lv * 3 + op] == 0 for op in range(3))

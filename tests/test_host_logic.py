@@ -44,7 +44,7 @@ def test_library_is_sm100a_and_has_no_cpu_fallback(mc):
     with pytest.raises(mc.McrgError):
         mc.Context(64, 1)
     lay = mc.capi.acc_layout()
-    assert lay.n_slots == 3 + 3 * 16 + 9 * 16 + 9 * 15
+    assert lay.n_slots == 3 + 3 * 16 + 9 * 16 + 9 * 15 + 9 * 15
     assert mc.capi.levels_full(128) == 6 and mc.capi.levels_full(4096) == 11 and mc.capi.levels_full(16384) == 13
 
 
@@ -74,6 +74,7 @@ def _fake_acc(mc, S_log):
                     acc[lay.slot_ss + lv * 9 + b * 3 + a] += int(S[lv, a]) * int(S[lv, b])
                     if lv >= 1:
                         acc[lay.slot_sbs + (lv - 1) * 9 + b * 3 + a] += int(S[lv, a]) * int(S[lv - 1, b])
+                        acc[lay.slot_sb0 + (lv - 1) * 9 + b * 3 + a] += int(S[lv, a]) * int(S[0, b])
     return acc
 
 

@@ -42,7 +42,7 @@ def thresholds(K):
     return t4.value, t8.value, (0xFFFFFFFF if K > 0 else 0)
 
 
-@pytest.mark.parametrize("L", [4, 8, 16, 32, 64, 128, 256])
+@pytest.mark.parametrize("L", [2, 4, 8, 16, 32, 64, 128, 256])
 def test_hot_start(emul, L):
     o = _libs.oracle()
     a = np.zeros((L, L), np.int32)
@@ -54,7 +54,7 @@ def test_hot_start(emul, L):
 
 
 @pytest.mark.parametrize("L,R,fuse,n_sweeps,K", [
-    (4, 4, 1, 3, KC), (4, 2, 1, 2, KC), (8, 8, 1, 3, KC), (8, 2, 2, 4, -0.3), (16, 4, 1, 2, KC), (16, 16, 3, 5, KC),
+    (2, 2, 1, 4, KC), (2, 2, 2, 3, -0.2), (4, 4, 1, 3, KC), (4, 2, 1, 2, KC), (8, 8, 1, 3, KC), (8, 2, 2, 4, -0.3), (16, 4, 1, 2, KC), (16, 16, 3, 5, KC),
     (32, 8, 2, 3, -0.6), (64, 64, 1, 2, KC), (64, 16, 2, 3, 0.35), (128, 32, 1, 2, KC), (128, 8, 4, 4, -0.44),
     (256, 64, 2, 2, KC), (512, 32, 1, 1, KC),
 ])
@@ -88,7 +88,7 @@ def test_sweep_from_ordered_start_low_temperature(emul):
     assert 0 < (a == -1).sum() < 200
 
 
-@pytest.mark.parametrize("L,R,Rn", [(4, 4, 2), (8, 2, 2), (16, 16, 4), (32, 8, 8), (64, 64, 16), (128, 16, 16),
+@pytest.mark.parametrize("L,R,Rn", [(2, 2, 2), (4, 4, 2), (8, 2, 2), (16, 16, 4), (32, 8, 8), (64, 64, 16), (128, 16, 16),
                                     (256, 32, 32), (512, 64, 64), (1024, 64, 32), (2048, 32, 64)])
 def test_measurement_pyramid(emul, L, R, Rn):
     seed, replica, t = 4242, 11, 123456789012
