@@ -8,7 +8,7 @@ Workload (BASELINE.json metric: spin-flip attempts/s at L=4096 with MCRG correla
   L = 4096 bit-packed lattices, the 5 couplings of train.cpp:25 x `--replicas-per-k` replicas on every GPU,
   one full measurement (correlators at all 12 levels of the b=2 pyramid + cross-correlator accumulation) after
   EVERY sweep (m = 1, as the reference measures after every update, mcrg.cpp:75-97).
-  One "step" = one measurement block: `--samples` x (measure + sweep) on every replica, then the ONE collective
+  One "step" = one measurement block: `--samples` (default 128) x (measure + sweep) on every replica, then the ONE collective
   of the path — an int64 all-reduce of the accumulator totals (mcrg.cpp:101-103).
   value = attempts of all ranks / max-over-ranks device time (CUDA events, state resident in HBM).
   e2e   = the same block through the C ABI with HOST buffers: every step uploads the replicas' configurations in
@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.02)
         except Exception as e:  # NVML missing: report that rather than inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -300,8 +300,13 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_SITE_DOMINANT * n_loc * L * L,
                      "kernel_ms": dom_ms, "kernel_share_of_sample": dom_ms / sample_ms if sample_ms > 0 else None,
                      "per_sample_ms": prof,
+                     "compute_bound": {"what": "Philox4x32-10 + 4-plane lazy compare, measured ceiling on this B200 "
+                                               "(profiles/microbench_pipes_r1.txt): 0.37 T calls/s; a sweep needs ~2.1 calls per 32 sites",
+                                       "ceiling_G_sites_per_s": 0.37e3 * 32 / 2.1,
+                                       "achieved_G_sites_per_s": n_loc * L * L / (dom_ms * 1e-3) / 1e9,
+                                       "frac": (n_loc * L * L / (dom_ms * 1e-3) / 1e9) / (0.37e3 * 32 / 2.1)},
                      "note": "1 bit/spin makes the compulsory traffic tiny: the kernel is INT/Philox-issue bound, not HBM bound "
-                             "(see DESIGN.md and profiles/)"},
+                             "(see DESIGN.md section 3.1 and profiles/)"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = host_procs(L)
@@ -327,7 +332,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=4096)
     ap.add_argument("--replicas-per-k", type=int, default=8)
-    ap.add_argument("--samples", type=int, default=32, help="measurement samples per step (block)")
+    ap.add_argument("--samples", type=int, default=128,
+                    help="measurement samples per step = one measurement block between collectives (the reference "
+                         "takes 1e4 samples per rank between its all-reduces, main.cpp:10-11 / mcrg.cpp:72-103)")
     ap.add_argument("--sweeps-per-sample", type=int, default=1)
     ap.add_argument("--strip-rows", type=int, default=0)
     ap.add_argument("--fuse-sweeps", type=int, default=1)

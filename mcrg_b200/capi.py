@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcrg_b200.so")
+LIB_PATH = os.environ.get("MCRG_LIB") or os.path.join(HERE, "libmcrg_b200.so")  # MCRG_LIB: A/B builds of the same library
 
 MAX_LEVELS = 15
 NOP = 3

@@ -53,8 +53,14 @@ struct mcrg_ctx {
     int device = 0, L = 0, W = 0, bits = 0, n_replicas = 0, n_bins = 1, full_levels = 0;
     uint64_t seed = 0;
     uint32_t replica_base = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // sweeps (and everything else)
+    cudaStream_t stream2 = nullptr;  // blocked-level pyramid of sample s, overlapped with the sweep of sample s+1
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_meas[2] = {nullptr, nullptr}, ev_pyr[2] = {nullptr, nullptr};
+    bool pyr_pending[2] = {false, false};
+    int overlap = 1;      // run the pyramid on stream2
+    int last_parity = 0;  // which level-1 / popcount buffer the last measurement used
+    size_t level1_words = 0, cnt_cells = 0;
     uint32_t *planes[2] = {nullptr, nullptr};
     int cur = 0;
     uint32_t *levels = nullptr;
@@ -112,12 +118,18 @@ int ensure_stage(mcrg_ctx *c, size_t ints) {
     return 0;
 }
 
-SweepArgs sweep_args(const mcrg_ctx *c, int R, int nsw, unsigned long long t_off) {
+// level-1 lattice and popcount cells are double-buffered by sample parity (see enqueue_sample)
+uint32_t *level_ptr(const mcrg_ctx *c, int lv, int parity) {
+    return c->levels + c->level_off[lv] + (lv == 1 ? (size_t)parity * c->level1_words : 0);
+}
+unsigned long long *cnt_ptr(const mcrg_ctx *c, int parity) { return c->cnt + (size_t)parity * c->cnt_cells; }
+
+SweepArgs sweep_args(const mcrg_ctx *c, int R, int nsw, unsigned long long t_off, int parity = 0) {
     SweepArgs a;
     a.src = c->planes[c->cur];
     a.dst = c->planes[1 - c->cur];
-    a.level1 = c->levels + c->level_off[1];
-    a.cnt = c->cnt;
+    a.level1 = level_ptr(c, 1, parity);
+    a.cnt = cnt_ptr(c, parity);
     a.T4 = c->T4;
     a.T8 = c->T8;
     a.anti = c->anti;
@@ -148,23 +160,44 @@ void enqueue_sweeps(mcrg_ctx *c, int n, unsigned long long t_off) {
     }
 }
 
+// make the main stream wait for every pyramid still in flight on stream2 (no-op when nothing is pending)
+void join_pyramids(mcrg_ctx *c) {
+    for (int p = 0; p < 2; ++p)
+        if (c->pyr_pending[p]) {
+            cudaStreamWaitEvent(c->stream, c->ev_pyr[p], 0);
+            c->pyr_pending[p] = false;
+        }
+}
+
 // enqueue: measure the current configuration at levels 0..n_lv (+ accumulate), fused with the first of
-// `m` sweeps; then the remaining m-1 sweeps.
-void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsigned long long t_off,
+// `m` sweeps; then the remaining m-1 sweeps.  The blocked-level kernels of sample s (k_level, k_tail) only read
+// the level-1 lattice and the popcount cells written by k_sweep0<MEASURE>; both are double-buffered by `parity`,
+// so they run on stream2 while the main stream already sweeps towards sample s+1.
+void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsigned long long t_off, int parity,
                     cudaEvent_t *probe = nullptr) {
+    const bool overlap = c->overlap && probe == nullptr;
+    cudaStream_t s_pyr = overlap ? c->stream2 : c->stream;
+    if (c->pyr_pending[parity]) {  // the pyramid of sample s-2 used this buffer pair
+        cudaStreamWaitEvent(c->stream, c->ev_pyr[parity], 0);
+        c->pyr_pending[parity] = false;
+    }
     const int first = m > 0 ? 1 : 0;
     const int R = choose_R(c, 2);
-    SweepArgs a = sweep_args(c, R, first, t_off);
+    SweepArgs a = sweep_args(c, R, first, t_off, parity);
     if (probe) cudaEventRecord(probe[0], c->stream);
     launch_sweep0(a, c->n_replicas, true, c->stream);
     if (probe) cudaEventRecord(probe[1], c->stream);
     if (first) c->cur ^= 1;
+    if (overlap) {
+        cudaEventRecord(c->ev_meas[parity], c->stream);
+        cudaStreamWaitEvent(s_pyr, c->ev_meas[parity], 0);
+    }
     int lv = 1;
     while (lv <= n_lv && (c->L >> lv) > TAIL_MAX_L) {
         LevelArgs la;
-        la.in = c->levels + c->level_off[lv];
-        la.out = lv < n_lv ? c->levels + c->level_off[lv + 1] : nullptr;
-        la.cnt = c->cnt;
+        la.in = level_ptr(c, lv, parity);
+        la.out = lv < n_lv ? level_ptr(c, lv + 1, parity) : nullptr;
+        la.cnt = cnt_ptr(c, parity);
         la.d_t = c->d_t;
         la.t_off = t_off;
         la.seed = c->seed;
@@ -173,14 +206,14 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
         la.level = lv;
         la.R = choose_Rn(la.Ln);
         la.strips = la.Ln / la.R;
-        launch_level(la, c->n_replicas, c->stream);
+        launch_level(la, c->n_replicas, s_pyr);
         ++lv;
     }
     TailArgs ta;
-    ta.in = lv <= n_lv ? c->levels + c->level_off[lv] : nullptr;
+    ta.in = lv <= n_lv ? level_ptr(c, lv, parity) : nullptr;
     ta.levels_out = c->levels;
     ta.level_off = c->d_level_off;
-    ta.cnt = c->cnt;
+    ta.cnt = cnt_ptr(c, parity);
     ta.S_out = c->S_out;
     ta.acc_lo = c->acc_lo;
     ta.acc_hi = c->acc_hi;
@@ -196,9 +229,14 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     ta.bin = bin;
     ta.accumulate = accumulate;
     if (probe) cudaEventRecord(probe[2], c->stream);
-    launch_tail(ta, c->n_replicas, c->stream);
+    launch_tail(ta, c->n_replicas, s_pyr);
     if (probe) cudaEventRecord(probe[3], c->stream);
+    if (overlap) {
+        cudaEventRecord(c->ev_pyr[parity], s_pyr);
+        c->pyr_pending[parity] = true;
+    }
     c->last_levels = n_lv;
+    c->last_parity = parity;
     c->measured = true;
     if (m > 1) enqueue_sweeps(c, m - 1, t_off + 1);
     if (probe) cudaEventRecord(probe[4], c->stream);
@@ -261,9 +299,19 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     if (const char *e = getenv("MCRG_USE_GRAPHS")) c->use_graphs = atoi(e);
     *out = c;  // so that a failure below can still be cleaned up by mcrg_ctx_destroy
     sweep0_max_smem();  // opt in to large dynamic shared memory once, outside any stream capture
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+        CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));  // small kernels first
+    }
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    for (int p = 0; p < 2; ++p) {
+        CK(cudaEventCreateWithFlags(&c->ev_meas[p], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_pyr[p], cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("MCRG_OVERLAP")) c->overlap = atoi(e);
     const size_t plane_words = (size_t)n_replicas * 2 * L * c->W;
     CK(cudaMalloc(&c->planes[0], plane_words * 4));
     CK(cudaMalloc(&c->planes[1], plane_words * 4));
@@ -271,16 +319,18 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     for (int lv = 1; lv <= (c->full_levels > 1 ? c->full_levels : 1); ++lv) {  // level 1 always exists: k_sweep0 writes it
         const int Ln = L >> lv;
         c->level_off[lv] = off;
-        size_t words = (size_t)n_replicas * Ln * nat_words(Ln);
-        off += (words + 3) & ~(size_t)3;  // keep every level 16-byte aligned for the 128-bit loads
+        size_t words = ((size_t)n_replicas * Ln * nat_words(Ln) + 3) & ~(size_t)3;  // 16-byte aligned for 128-bit loads
+        if (lv == 1) c->level1_words = words;
+        off += (lv == 1 ? 2 : 1) * words;  // level 1 is double-buffered
     }
     CK(cudaMalloc(&c->levels, (off + 4) * 4));
     CK(cudaMemsetAsync(c->levels, 0, (off + 4) * 4, c->stream));
     CK(cudaMalloc(&c->d_level_off, sizeof(c->level_off)));
     CK(cudaMemcpyAsync(c->d_level_off, c->level_off, sizeof(c->level_off), cudaMemcpyHostToDevice, c->stream));
     const size_t n_cnt = (size_t)n_replicas * (MAX_LEVELS + 1) * 4;
-    CK(cudaMalloc(&c->cnt, n_cnt * 8));
-    CK(cudaMemsetAsync(c->cnt, 0, n_cnt * 8, c->stream));
+    c->cnt_cells = n_cnt;
+    CK(cudaMalloc(&c->cnt, 2 * n_cnt * 8));
+    CK(cudaMemsetAsync(c->cnt, 0, 2 * n_cnt * 8, c->stream));
     CK(cudaMalloc(&c->S_out, n_cnt * 8));
     CK(cudaMemsetAsync(c->S_out, 0, n_cnt * 8, c->stream));
     const size_t n_acc = (size_t)n_replicas * n_bins * N_SLOTS;
@@ -307,6 +357,7 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     destroy_graphs(c);
     cudaFree(c->planes[0]);
     cudaFree(c->planes[1]);
@@ -324,6 +375,11 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int p = 0; p < 2; ++p) {
+        if (c->ev_meas[p]) cudaEventDestroy(c->ev_meas[p]);
+        if (c->ev_pyr[p]) cudaEventDestroy(c->ev_pyr[p]);
+    }
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -459,7 +515,7 @@ int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *c, int replica, int level, int32
     const size_t per = (size_t)Ln * Ln;
     int rc = ensure_stage(c, per);
     if (rc) return rc;
-    launch_unpackN(c->levels + c->level_off[level] + (size_t)replica * Ln * nat_words(Ln), c->stage, Ln, 1, c->stream);
+    launch_unpackN(level_ptr(c, level, c->last_parity) + (size_t)replica * Ln * nat_words(Ln), c->stage, Ln, 1, c->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host, c->stage, per * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -498,7 +554,8 @@ int mcrg_measure(mcrg_ctx *c, int max_levels, int64_t *S, int *n_lv_out) {
     if (!c) return fail(MCRG_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     const int n_lv = clamp_levels(c, max_levels);
-    enqueue_sample(c, n_lv, 0, 0, 0, 0);
+    enqueue_sample(c, n_lv, 0, 0, 0, 0, 0);
+    join_pyramids(c);
     CK(cudaGetLastError());
     if (n_lv_out) *n_lv_out = n_lv;
     if (S) {
@@ -545,7 +602,8 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
             if (it == c->graphs.end()) {
                 cudaGraph_t g = nullptr;
                 CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m);
+                for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s & 1);
+                join_pyramids(c);  // every graph is self-contained: stream2 joins back before the capture ends
                 launch_advance_t(c->d_t, (unsigned long long)chunk * m, c->stream);
                 cudaError_t e = cudaStreamEndCapture(c->stream, &g);
                 if (e != cudaSuccess) {
@@ -567,6 +625,8 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
                 if (m > 1) flips_per_sample += (m - 1 + c->fuse_sweeps - 1) / c->fuse_sweeps;
                 if ((chunk * flips_per_sample) & 1) c->cur ^= 1;
                 c->last_levels = n_lv;
+                c->last_parity = (chunk - 1) & 1;
+                c->measured = true;
             }
             CK(cudaGraphLaunch(it->second, c->stream));
             c->t_host += (unsigned long long)chunk * m;
@@ -575,7 +635,8 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
     }
     const int rest = n_samples - done;
     if (rest > 0) {
-        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m);
+        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s & 1);
+        join_pyramids(c);
         if (m > 0) launch_advance_t(c->d_t, (unsigned long long)rest * m, c->stream);
         c->t_host += (unsigned long long)rest * m;
     }
@@ -591,7 +652,7 @@ int mcrg_profile_kernels(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int 
     const int m = sweeps_per_sample;
     std::vector<cudaEvent_t> ev((size_t)n_samples * 5);
     for (auto &e : ev) CK(cudaEventCreate(&e));
-    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, &ev[(size_t)s * 5]);
+    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, s & 1, &ev[(size_t)s * 5]);
     if (m > 0) launch_advance_t(c->d_t, (unsigned long long)n_samples * m, c->stream);
     c->t_host += (unsigned long long)n_samples * m;
     CK(cudaGetLastError());

@@ -13,6 +13,10 @@
 //                      accumulation of mcrg.cpp:86-97 (S, S(n) x S(n-1), S(n) x S(n)) into exact 128-bit sums.
 #include "kernels.cuh"
 
+#ifndef MCRG_SWEEP_MIN_BLOCKS
+#define MCRG_SWEEP_MIN_BLOCKS 4
+#endif
+
 namespace mcrg {
 
 namespace {
@@ -104,41 +108,59 @@ __device__ __forceinline__ U4 mc_philox(uint64_t seed, uint32_t word_id, uint32_
 }
 
 struct McQueue {
-    int *cnt;        // two counters, used alternately by successive half-sweeps
-    uint32_t *ent;   // [cap][3]: tile word offset, undecided lanes, selector (A==1 lanes)
-    int cap;
+    uint32_t *ent;   // [warp][cap][3]: tile word offset, undecided lanes, selector (A==1 lanes)
+    int cap;         // entries per warp
 };
 
+// finish one word whose lanes `eq` are still undecided after planes [0, 4*j0): calls j0, j0+1, ... (rare path)
+__device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0, const McTable *tab, uint64_t seed,
+                                              uint32_t word_id, uint32_t replica, uint32_t t_lo, uint32_t c3_base) {
+    uint32_t lt = 0;
+    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox(seed, word_id, replica, t_lo, c3_base, j), tab, 4 * j, sel, eq, lt);
+    return lt;
+}
+
+// One half-sweep (colour c) over local rows [lr_lo, lr_lo + nrows).  A thread keeps its column w and walks down the
+// rows with a constant stride, so word offsets are incremental.  Words that still have undecided lanes after the 8
+// planes of pass 1 are appended to a queue PRIVATE TO THE WARP (slot = warp-uniform running count + rank in the
+// ballot: no atomics, no shuffles) and finished densely by the same warp — only __syncwarp() between the passes.
 __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
-                                              const McTable *tab, const McQueue &q, int parity, uint64_t seed,
-                                              uint32_t replica, unsigned long long sweep) {
+                                              const McTable *tab, const McQueue &q, uint64_t seed, uint32_t replica,
+                                              unsigned long long sweep) {
     const int W = s.W, o = 1 - c;
-    const int n = nrows << lw;
     const uint32_t t_lo = (uint32_t)sweep;
     const uint32_t c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
     uint32_t *plane_c = s.base + c * s.rows * W;
     const uint32_t *plane_o = s.base + o * s.rows * W;
-    int *cnt = q.cnt + parity;
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int idx = base + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    uint32_t *my_q = q.ent + 3 * q.cap * warp;  // this warp's segment: q.cap entries
+    const int w = threadIdx.x & (W - 1);
+    const int row_step = blockDim.x >> lw;  // blockDim is a multiple of W (launch_sweep0)
+    const int d_up = ((w + 1) & (W - 1)) - w, d_dn = ((w - 1) & (W - 1)) - w;
+    const int lr_hi = lr_lo + nrows;
+    const int n_iter = (nrows + row_step - 1) / row_step;  // identical for every thread: ballots are full-warp
+    const uint32_t wid_base = (uint32_t)(c * s.L * W + w);
+    int lr = lr_lo + (threadIdx.x >> lw);
+    int n_queued = 0;  // warp-uniform
+    for (int it = 0; it < n_iter; ++it, lr += row_step) {
         uint32_t eq = 0, sel = 0, off = 0;
-        if (idx < n) {
-            const int lr = lr_lo + (idx >> lw), w = idx & (W - 1);
+        if (lr < lr_hi) {
             off = (uint32_t)(lr * W + w);
             const int y = (s.y_first + lr) & (s.L - 1);
             const uint32_t t = plane_c[off];
             const uint32_t u = plane_o[off - W], d = plane_o[off + W], n0 = plane_o[off];
             uint32_t n1;
-            if ((y + c) & 1) n1 = shift_up_index(n0, plane_o[lr * W + ((w + 1) & (W - 1))], s.bits, s.mask);
-            else n1 = shift_down_index(n0, plane_o[lr * W + ((w - 1) & (W - 1))], s.bits, s.mask);
+            if ((y + c) & 1) n1 = shift_up_index(n0, plane_o[off + d_up], s.bits, s.mask);
+            else n1 = shift_down_index(n0, plane_o[off + d_dn], s.bits, s.mask);
             const uint32_t a1 = t ^ u ^ anti, a2 = t ^ d ^ anti, a3 = t ^ n0 ^ anti, a4 = t ^ n1 ^ anti;
             const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
             const uint32_t ge2 = c12 | c34 | (x12 & x34);
-            sel = (x12 ^ x34) & ~(c12 | c34) & s.mask;         // A == 1
-            eq = (sel | ~(a1 | a2 | a3 | a4)) & s.mask;        // A == 1 or A == 0: lanes that need a random number
+            sel = (x12 ^ x34) & ~(c12 | c34) & s.mask;   // A == 1
+            eq = (sel | ~(a1 | a2 | a3 | a4)) & s.mask;  // A == 1 or A == 0: lanes that need a random number
             uint32_t lt = 0;
             if (eq) {
-                const uint32_t word_id = (uint32_t)((c * s.L + y) * W + w);
+                const uint32_t word_id = wid_base + ((uint32_t)y << lw);
                 const U4 r0 = mc_philox(seed, word_id, replica, t_lo, c3_base, 0);
                 const U4 r1 = mc_philox(seed, word_id, replica, t_lo, c3_base, 1);
                 mc_compare4(r0, tab, 0, sel, eq, lt);
@@ -146,52 +168,36 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
             }
             plane_c[off] = t ^ ((ge2 | lt) & s.mask);
         }
-        // warp-aggregated append of the words that still have undecided lanes
-        const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);
-        if (pend) {
-            const int lane = threadIdx.x & 31;
-            int slot = 0;
-            if (lane == (__ffs(pend) - 1)) slot = atomicAdd(cnt, __popc(pend));
-            slot = __shfl_sync(0xFFFFFFFFu, slot, __ffs(pend) - 1) + __popc(pend & ((1u << lane) - 1u));
-            if (eq != 0u) {
-                if (slot < q.cap) {
-                    q.ent[3 * slot + 0] = off;
-                    q.ent[3 * slot + 1] = eq;
-                    q.ent[3 * slot + 2] = sel;
-                } else {  // queue full (cannot happen for equilibrium-like data; kept for exactness): finish inline
-                    const int lr = (int)off >> lw, w = (int)off & (W - 1);
-                    const int y = (s.y_first + lr) & (s.L - 1);
-                    const uint32_t word_id = (uint32_t)((c * s.L + y) * W + w);
-                    uint32_t lt = 0;
-                    for (int j = 2; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox(seed, word_id, replica, t_lo, c3_base, j), tab, 4 * j, sel, eq, lt);
-                    plane_c[off] ^= lt;
-                }
+        const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);  // ~10 % of the words
+        if (eq != 0u) {
+            const int slot = n_queued + __popc(pend & lanes_below);
+            if (slot < q.cap) {
+                my_q[3 * slot + 0] = off;
+                my_q[3 * slot + 1] = eq;
+                my_q[3 * slot + 2] = sel;
+            } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
+                const int y = (s.y_first + ((int)off >> lw)) & (s.L - 1);
+                plane_c[off] ^= mc_finish(eq, sel, 2, tab, seed, wid_base + ((uint32_t)y << lw), replica, t_lo, c3_base);
             }
         }
+        n_queued += __popc(pend);
     }
-    __syncthreads();
-    const int total = min(*cnt, q.cap);
-    if (threadIdx.x == 0) q.cnt[parity ^ 1] = 0;  // the other counter is idle now: reset it for the next half-sweep
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const uint32_t off = q.ent[3 * e + 0];
-        uint32_t eq = q.ent[3 * e + 1];
-        const uint32_t sel = q.ent[3 * e + 2];
-        const int lr = (int)off >> lw, w = (int)off & (W - 1);
-        const int y = (s.y_first + lr) & (s.L - 1);
-        const uint32_t word_id = (uint32_t)((c * s.L + y) * W + w);
-        uint32_t lt = 0;
-        for (int j = 2; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox(seed, word_id, replica, t_lo, c3_base, j), tab, 4 * j, sel, eq, lt);
-        plane_c[off] ^= lt;
+    __syncwarp();
+    const int total = min(n_queued, q.cap);
+    for (int e = lane; e < total; e += 32) {
+        const uint32_t off = my_q[3 * e + 0];
+        const int y = (s.y_first + ((int)off >> lw)) & (s.L - 1);
+        const uint32_t word_id = (uint32_t)(c * s.L * W) + ((uint32_t)y << lw) + (off & (uint32_t)(W - 1));
+        plane_c[off] ^= mc_finish(my_q[3 * e + 1], my_q[3 * e + 2], 2, tab, seed, word_id, replica, t_lo, c3_base);
     }
     __syncthreads();
 }
 
 template <bool MEASURE>
-__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_sweep0(const SweepArgs a) {
+__global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0(const SweepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[4];
     __shared__ __align__(16) McTable tab;
-    __shared__ int q_cnt[2];
     const int r = blockIdx.y, strip = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
     const int rows = a.R + 2 * a.H;
@@ -208,7 +214,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_sweep0(const SweepArgs a) 
     stage_rows(s0_plane(s, 0), src_r, s.y_first, rows, W, L);
     stage_rows(s0_plane(s, 1), src_r + (size_t)L * W, s.y_first, rows, W, L);
     if (MEASURE && threadIdx.x < 4) red[threadIdx.x] = 0;
-    if (threadIdx.x < 2) q_cnt[threadIdx.x] = 0;
     if (a.nsw > 0) {
         for (int k = threadIdx.x; k < 64; k += blockDim.x) {  // blockDim may be as small as 32
             const uint32_t T = (k & 1) ? a.T8[r] : a.T4[r];
@@ -240,12 +245,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_sweep0(const SweepArgs a) 
 
     if (a.nsw > 0) {
         McQueue q;
-        q.cnt = q_cnt;
         q.ent = smem + 2 * rows * W;
-        q.cap = sweep0_queue_cap(rows * W);
+        q.cap = sweep0_queue_cap(rows * W, blockDim.x >> 5);
         const uint32_t anti = a.anti[r];
         for (int h = 0; h < 2 * a.nsw; ++h)
-            mc_half_sweep(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, h & 1, a.seed, replica,
+            mc_half_sweep(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, a.seed, replica,
                           t + (unsigned long long)(h >> 1));
         uint32_t *dst_r = a.dst + (size_t)r * 2 * L * W;
         unstage_rows(dst_r, s0_plane(s, 0) + a.H * W, y0, a.R, W, L);
@@ -497,9 +501,24 @@ int g_max_smem = -1;
 
 }  // namespace
 
+static int pick_threads(long long work_items, int max_threads) {
+    long long t = (work_items + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > max_threads) t = max_threads;
+    return (int)t;
+}
+
+int sweep0_threads(int L, int R, int H) {
+    const int W = l0_words(L);
+    int threads = pick_threads((long long)(R + 2 * H) * W, SWEEP_THREADS);
+    if (threads < W) threads = W;  // mc_half_sweep: a thread owns one column, blockDim is a multiple of W
+    return threads;
+}
+
 size_t sweep0_smem_bytes(int L, int R, int H) {
     const int words = (R + 2 * H) * l0_words(L);
-    return ((size_t)2 * words + (size_t)3 * sweep0_queue_cap(words)) * sizeof(uint32_t);
+    const int warps = sweep0_threads(L, R, H) / 32;
+    return ((size_t)2 * words + (size_t)3 * warps * sweep0_queue_cap(words, warps)) * sizeof(uint32_t);
 }
 
 int sweep0_max_smem() {
@@ -518,18 +537,12 @@ int sweep0_max_smem() {
     return g_max_smem;
 }
 
-static int pick_threads(long long work_items, int max_threads) {
-    long long t = (work_items + 31) / 32 * 32;
-    if (t < 32) t = 32;
-    if (t > max_threads) t = max_threads;
-    return (int)t;
-}
 
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st) {
     sweep0_max_smem();
     const size_t smem = sweep0_smem_bytes(a.L, a.R, a.H);
     const dim3 grid(a.strips, n_replicas);
-    const int threads = pick_threads((long long)(a.R + 2 * a.H) * a.W, SWEEP_THREADS);
+    const int threads = sweep0_threads(a.L, a.R, a.H);
     if (measure) k_sweep0<true><<<grid, threads, smem, st>>>(a);
     else k_sweep0<false><<<grid, threads, smem, st>>>(a);
 }

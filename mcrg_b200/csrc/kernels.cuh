@@ -11,9 +11,10 @@ constexpr int MAX_LEVELS = 15;          // L <= 2^15; levels 0..14 at most
 constexpr int NOP = 3;                  // even operators: nn, nnn, plaquette
 constexpr int TAIL_MAX_L = 256;         // blocked lattices up to this size finish inside one CTA's shared memory
 constexpr int SWEEP_THREADS = 256;
-// capacity of the "still undecided after 8 bit planes" queue of a strip with `words` words per colour
-// (expected fill: ~10 % of the words of one colour)
-MCRG_HD int sweep0_queue_cap(int words) { return words / 4 > 64 ? words / 4 : 64; }
+// capacity of a warp's "still undecided after 8 bit planes" queue for a strip with `words` words per colour
+// (expected fill: ~10 % of the words)
+// per warp: a quarter of the words a warp handles in one half-sweep, at least 16 entries
+MCRG_HD int sweep0_queue_cap(int words, int warps) { const int c = (words / warps + 3) / 4; return c > 16 ? c : 16; }
 
 // accumulator slots (per replica, per bin), all exact 128-bit integers (lo: uint64, hi: int64)
 constexpr int SLOT_N = 0;                                    // samples
@@ -85,6 +86,7 @@ void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas,
 void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st);
 void launch_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int n_replicas, cudaStream_t st);
 size_t sweep0_smem_bytes(int L, int R, int H);
+int sweep0_threads(int L, int R, int H);
 int sweep0_max_smem();
 
 }  // namespace mcrg
