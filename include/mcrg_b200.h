@@ -97,6 +97,19 @@ int mcrg_run(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, int max_levels
  * tail kernel}.  The chain and the accumulators advance exactly as in mcrg_run. */
 int mcrg_profile_kernels(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, int max_levels, float out_ms[4]);
 
+/* ---- RGNN: consumer of the sampler ---------------------------------------------------------- */
+/* RenormalizationGroupNeuralNetwork::set_weights (rgnn.cpp:38-42): W is the 2x2 filter, column-major (W[k*2+r] = W(r,k)) */
+int mcrg_rgnn_set_weights(mcrg_ctx *ctx, const double *W);
+/* scalar_output (rgnn.cpp:281-307) and calc_gradient_scalar_output (rgnn.cpp:310-339, central differences with step
+ * h) of every replica's current configuration: u[replica], grad[replica][4] (column-major 2x2).  Either may be NULL. */
+int mcrg_rgnn_eval(mcrg_ctx *ctx, double h, double *u, double *grad);
+/* the sample loop of train_scalar_output for one lattice size (rgnn.cpp:106-123): n_samples x { sweeps_per_sample
+ * sweeps, then u and grad of the new configuration added to this replica's sums }.
+ * sums per replica: { sum u, sum u^2, sum grad(0,0), grad(1,0), grad(0,1), grad(1,1) }. */
+int mcrg_rgnn_run(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, double h);
+int mcrg_rgnn_accumulators_reset(mcrg_ctx *ctx);
+int mcrg_rgnn_accumulators_get(mcrg_ctx *ctx, double *out /* [replica][6] */);
+
 /* ---- accumulators (mcrg.cpp:53-70 containers), exact 128-bit integers ------------------------------------ */
 typedef struct {
     int n_slots, n_dslots;

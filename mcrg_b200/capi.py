@@ -61,6 +61,11 @@ def lib():
         l.mcrg_observables.argtypes = [vp, vp, vp, vp, vp]
         l.mcrg_run.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         l.mcrg_profile_kernels.argtypes = [vp, C.c_int, C.c_int, C.c_int, P(C.c_float)]
+        l.mcrg_rgnn_set_weights.argtypes = [vp, vp]
+        l.mcrg_rgnn_eval.argtypes = [vp, C.c_double, vp, vp]
+        l.mcrg_rgnn_run.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        l.mcrg_rgnn_accumulators_reset.argtypes = [vp]
+        l.mcrg_rgnn_accumulators_get.argtypes = [vp, vp]
         l.mcrg_accumulators_layout.argtypes = [P(AccLayout)]
         l.mcrg_accumulators_reset.argtypes = [vp]
         l.mcrg_accumulators_get.argtypes = [vp, vp, vp, vp]
@@ -207,6 +212,31 @@ class Context:
         out = (C.c_float * 4)()
         _check(lib().mcrg_profile_kernels(self._h, n_samples, sweeps_per_sample, max_levels, out))
         return dict(sweep_measure=out[0], sweep_only=out[1], level=out[2], tail=out[3])
+
+    # ---- RGNN
+    def rgnn_set_weights(self, W):
+        """W: 2x2, W[r, k] (set_weights of rgnn.cpp:38-42); sent column-major."""
+        W = np.ascontiguousarray(np.asarray(W, np.float64).reshape(2, 2).T)  # column-major bytes
+        _check(lib().mcrg_rgnn_set_weights(self._h, W.ctypes.data))
+
+    def rgnn_eval(self, h=1e-4):
+        """-> (u[replica], grad[replica, r, k]) of the current configurations."""
+        u = np.zeros(self.n_replicas, np.float64)
+        g = np.zeros((self.n_replicas, 4), np.float64)
+        _check(lib().mcrg_rgnn_eval(self._h, h, u.ctypes.data, g.ctypes.data))
+        return u, g.reshape(-1, 2, 2).transpose(0, 2, 1).copy()  # column-major -> [r, k]
+
+    def rgnn_run(self, n_samples, sweeps_per_sample=1, h=1e-4):
+        _check(lib().mcrg_rgnn_run(self._h, n_samples, sweeps_per_sample, h))
+
+    def rgnn_reset(self):
+        _check(lib().mcrg_rgnn_accumulators_reset(self._h))
+
+    def rgnn_sums(self):
+        """-> [replica, 6] = sum u, sum u^2, sum grad (column-major 2x2)."""
+        out = np.zeros((self.n_replicas, 6), np.float64)
+        _check(lib().mcrg_rgnn_accumulators_get(self._h, out.ctypes.data))
+        return out
 
     # ---- accumulators
     def reset_accumulators(self):

@@ -74,6 +74,7 @@ struct mcrg_ctx {
     uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr;
     unsigned long long *d_t = nullptr;
     unsigned long long t_host = 0;
+    double *rgnn_W = nullptr, *rgnn_acc = nullptr, *rgnn_u = nullptr, *rgnn_grad = nullptr;
     int32_t *stage = nullptr;
     size_t stage_ints = 0;
     int last_levels = 0;
@@ -340,6 +341,12 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     CK(cudaMalloc(&c->T4, n_replicas * 4));
     CK(cudaMalloc(&c->T8, n_replicas * 4));
     CK(cudaMalloc(&c->anti, n_replicas * 4));
+    CK(cudaMalloc(&c->rgnn_W, 4 * sizeof(double)));
+    CK(cudaMalloc(&c->rgnn_acc, (size_t)n_replicas * 6 * sizeof(double)));
+    CK(cudaMalloc(&c->rgnn_u, (size_t)n_replicas * sizeof(double)));
+    CK(cudaMalloc(&c->rgnn_grad, (size_t)n_replicas * 4 * sizeof(double)));
+    CK(cudaMemsetAsync(c->rgnn_W, 0, 4 * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->rgnn_acc, 0, (size_t)n_replicas * 6 * sizeof(double), c->stream));
     CK(cudaMalloc(&c->d_t, 8));
     CK(cudaMemsetAsync(c->d_t, 0, 8, c->stream));
     launch_init_cold(c->planes[0], L, n_replicas, c->stream);
@@ -372,6 +379,10 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->T8);
     cudaFree(c->anti);
     cudaFree(c->d_t);
+    cudaFree(c->rgnn_W);
+    cudaFree(c->rgnn_acc);
+    cudaFree(c->rgnn_u);
+    cudaFree(c->rgnn_grad);
     cudaFree(c->stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -669,6 +680,58 @@ int mcrg_profile_kernels(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int 
     out_ms[1] = (float)(acc[3] / n_samples);  // k_sweep0<false> launches after the measurement
     out_ms[2] = (float)(acc[1] / n_samples);  // k_level launches
     out_ms[3] = (float)(acc[2] / n_samples);  // k_tail
+    return 0;
+}
+
+int mcrg_rgnn_set_weights(mcrg_ctx *c, const double *W) {
+    if (!c || !W) return fail(MCRG_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->rgnn_W, W, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // W may be a temporary on the caller's side
+    return 0;
+}
+
+int mcrg_rgnn_eval(mcrg_ctx *c, double h, double *u, double *grad) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (!(h > 0.0)) return fail(MCRG_ERR_ARG, "h must be positive");
+    CK(cudaSetDevice(c->device));
+    launch_rgnn(c->planes[c->cur], c->L, c->n_replicas, c->rgnn_W, h, c->rgnn_u, c->rgnn_grad, c->rgnn_acc, 0, c->stream);
+    CK(cudaGetLastError());
+    if (u) CK(cudaMemcpyAsync(u, c->rgnn_u, (size_t)c->n_replicas * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (grad) CK(cudaMemcpyAsync(grad, c->rgnn_grad, (size_t)c->n_replicas * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mcrg_rgnn_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, double h) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (n_samples < 0 || sweeps_per_sample < 0) return fail(MCRG_ERR_ARG, "negative count");
+    if (!(h > 0.0)) return fail(MCRG_ERR_ARG, "h must be positive");
+    CK(cudaSetDevice(c->device));
+    for (int s = 0; s < n_samples; ++s) {
+        if (sweeps_per_sample > 0) enqueue_sweeps(c, sweeps_per_sample, (unsigned long long)s * sweeps_per_sample);
+        launch_rgnn(c->planes[c->cur], c->L, c->n_replicas, c->rgnn_W, h, nullptr, nullptr, c->rgnn_acc, 1, c->stream);
+    }
+    if (n_samples > 0 && sweeps_per_sample > 0) {
+        launch_advance_t(c->d_t, (unsigned long long)n_samples * sweeps_per_sample, c->stream);
+        c->t_host += (unsigned long long)n_samples * sweeps_per_sample;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mcrg_rgnn_accumulators_reset(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->rgnn_acc, 0, (size_t)c->n_replicas * 6 * sizeof(double), c->stream));
+    return 0;
+}
+
+int mcrg_rgnn_accumulators_get(mcrg_ctx *c, double *out) {
+    if (!c || !out) return fail(MCRG_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->rgnn_acc, (size_t)c->n_replicas * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

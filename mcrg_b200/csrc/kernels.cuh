@@ -79,6 +79,8 @@ void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_
 void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st);
 void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st);
 void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st);
+void launch_rgnn(const uint32_t *planes, int L, int n_replicas, const double *W, double h, double *u_out, double *grad_out,
+                 double *acc, int accumulate, cudaStream_t st);
 void launch_advance_t(unsigned long long *d_t, unsigned long long by, cudaStream_t st);
 void launch_init_hot(uint32_t *planes, int L, int n_replicas, uint64_t seed, uint32_t replica_base, cudaStream_t st);
 void launch_init_cold(uint32_t *planes, int L, int n_replicas, cudaStream_t st);

@@ -2,11 +2,13 @@
 //   mcrg_app exponent N K n_eq n_samples            -> MonteCarloRenormalizationGroup::calc_critical_exponent
 //   mcrg_app kc L K0 n_iterations n_eq n_samples    -> MonteCarloRenormalizationGroup::locate_critical_point
 //   mcrg_app lattice N K n_updates                  -> Lattice / IsingModel fine-grained calls (prints observables)
+//   mcrg_app train L K n_cycles n_samples n_eq      -> RenormalizationGroupNeuralNetwork::train_scalar_output
 // Environment: MCRG_REPLICAS, MCRG_SWEEPS_PER_UPDATE, MCRG_SEED, MCRG_DEVICE, MCRG_QUIET.
 #include <cstdlib>
 #include <cstring>
 
 #include "mcrg.hpp"
+#include "rgnn.hpp"
 
 int main(int argc, char **argv) {
     MPI_Init(NULL, NULL);
@@ -43,6 +45,14 @@ int main(int argc, char **argv) {
                 }
             printf("RESULT Snn %.0f %.0f Snnn %.0f %.0f E %.12f M %.0f sum %lld\n", S(0), snn, S(1), snnn, ising.calc_energy(lat),
                    ising.calc_magnetization(lat), lat->sum_spins());
+        } else if (!strcmp(argv[1], "train") && argc == 7) {
+            // mcrg_app train L K n_cycles n_samples n_eq  — train.cpp:19-31 with W0 = [.5 -.5; .5 -.5], h = 1e-4, eta = 1e-3
+            mat W0(2, 2);
+            W0(0, 0) = 0.5; W0(0, 1) = -0.5; W0(1, 0) = 0.5; W0(1, 1) = -0.5;
+            RenormalizationGroupNeuralNetwork net(2);
+            net.set_weights(W0);
+            net.train_scalar_output(atoi(argv[2]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atof(argv[3]), 1e-4, 1e-3);
+            printf("RESULT final_mse %.10e W %.10f %.10f %.10f %.10f\n", net.final_mse_, net.W_(0, 0), net.W_(0, 1), net.W_(1, 0), net.W_(1, 1));
         } else {
             fprintf(stderr, "bad arguments\n");
             return 2;

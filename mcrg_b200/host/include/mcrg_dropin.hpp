@@ -148,4 +148,36 @@ private:
     std::shared_ptr<Lattice> block_spin_transformation(std::shared_ptr<Lattice> pLattice);
 };
 
+// ---- rgnn.hpp:7-66 -----------------------------------------------------------------------------------------
+class RenormalizationGroupNeuralNetwork {
+public:
+    RenormalizationGroupNeuralNetwork(int b);
+    ~RenormalizationGroupNeuralNetwork() {}
+
+    int n_processes_;
+    int rank_;
+    int b_;
+    int t_;
+    double eta_;
+    double beta1_;
+    double beta2_;
+    double epsilon_;
+    double w_;
+    mat m_;
+    mat v_;
+    mat W_;
+    FILE *fptr_;
+
+    double final_mse_;
+
+    void initialize();
+    void set_weights(const mat &W);
+    void train_scalar_output(int L, int n_cycles, int n_samples, int n_samples_eq, double T, double h, double eta);
+    void test_scalar_output(int L, int n_samples, int n_samples_eq, double K0, double DeltaK);
+    double scalar_output(const imat &input_spins);
+    void apply_filter(mat &input);
+    mat calc_gradient_scalar_output(double h, const imat &input_spins);
+    void update_weights(double eta, const mat &gradient);
+};
+
 #endif

@@ -506,3 +506,200 @@ std::shared_ptr<Lattice> MonteCarloRenormalizationGroup::block_spin_transformati
     ck(mcrg_get_level_spins_i32_colmajor(b->ctx, 0, 1, block_spins.data()), "mcrg_get_level_spins_i32_colmajor");
     return std::shared_ptr<Lattice>(new Lattice(pLattice->a_ * b_, block_spins));
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// RenormalizationGroupNeuralNetwork  (rgnn.cpp) — the consumer of the sampler; SURVEY 8f rank 2
+// ---------------------------------------------------------------------------------------------------------
+
+RenormalizationGroupNeuralNetwork::RenormalizationGroupNeuralNetwork(int b) {
+    n_processes_ = settings().replicas;  // device chains stand in for the MPI ranks
+    rank_ = 0;
+    b_ = b;
+    beta1_ = 0.9;
+    beta2_ = 0.999;
+    epsilon_ = 1E-8;
+    eta_ = 0.0;
+    w_ = 0.0;
+    fptr_ = NULL;
+    final_mse_ = 0.0;
+    if (b != 2) throw std::invalid_argument("mcrg_b200: only b = 2 filters are implemented on the device");
+    initialize();
+}
+
+void RenormalizationGroupNeuralNetwork::initialize() {
+    // rgnn.cpp:19-35: N(0, 0.3^2) weights in (i outer, j inner) order, ADAM state cleared
+    W_.resize(b_, b_);
+    for (int i = 0; i < b_; ++i)
+        for (int j = 0; j < b_; ++j) W_(i, j) = rand_weight();
+    t_ = 1;
+    m_.resize(b_, b_);
+    v_.resize(b_, b_);
+    m_.setZero();
+    v_.setZero();
+}
+
+void RenormalizationGroupNeuralNetwork::set_weights(const mat &W) { W_ = W; }
+
+void RenormalizationGroupNeuralNetwork::apply_filter(mat &input) {
+    // rgnn.cpp:290-307: one filter application, each b x b block B -> entrywise L1 norm of the matrix product W*B.
+    // Host helper for the "Example Flow" dump; the sampling loops evaluate the whole pyramid on the device.
+    const int N = (int)input.rows() / b_;
+    mat output(N, N);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double l1 = 0.0;
+            for (int c = 0; c < b_; ++c)
+                for (int r = 0; r < b_; ++r) {
+                    double acc = 0.0;
+                    for (int k = 0; k < b_; ++k) acc += W_(r, k) * input(b_ * i + k, b_ * j + c);
+                    l1 += std::fabs(acc);
+                }
+            output(i, j) = l1;
+        }
+    input = output;
+}
+
+namespace {
+struct RgnnEval {
+    double u;
+    double g[4];  // column-major 2x2
+};
+RgnnEval device_rgnn(const imat &spins, const mat &W, double h) {
+    const int N = (int)spins.rows();
+    DeviceBatch b(N, 1, mcrg_b200::g_next_lattice_id.fetch_add(1));
+    ck(mcrg_set_spins_i32_colmajor(b.ctx, 0, 1, spins.data()), "mcrg_set_spins_i32_colmajor");
+    ck(mcrg_rgnn_set_weights(b.ctx, W.data()), "mcrg_rgnn_set_weights");
+    RgnnEval e;
+    ck(mcrg_rgnn_eval(b.ctx, h, &e.u, e.g), "mcrg_rgnn_eval");
+    return e;
+}
+}  // namespace
+
+double RenormalizationGroupNeuralNetwork::scalar_output(const imat &input_spins) {
+    return device_rgnn(input_spins, W_, 1e-4).u;  // rgnn.cpp:281-288
+}
+
+mat RenormalizationGroupNeuralNetwork::calc_gradient_scalar_output(double h, const imat &input_spins) {
+    const RgnnEval e = device_rgnn(input_spins, W_, h);  // rgnn.cpp:310-339
+    mat grad(b_, b_);
+    for (int k = 0; k < 4; ++k) grad.data()[k] = e.g[k];
+    return grad;
+}
+
+void RenormalizationGroupNeuralNetwork::update_weights(double eta, const mat &gradient) {
+    // rgnn.cpp:342-357: ADAM with bias-corrected step size
+    eta_ = eta * std::sqrt(1.0 - std::pow(beta2_, t_)) / (1.0 - std::pow(beta1_, t_));
+    for (int i = 0; i < b_; ++i)
+        for (int j = 0; j < b_; ++j) {
+            m_(i, j) = beta1_ * m_(i, j) + (1.0 - beta1_) * gradient(i, j);
+            v_(i, j) = beta2_ * v_(i, j) + (1.0 - beta2_) * gradient(i, j) * gradient(i, j);
+            W_(i, j) -= eta_ * m_(i, j) / (std::sqrt(v_(i, j)) + epsilon_);
+        }
+    t_ += 1;
+}
+
+namespace {
+// sums over all chains of one batch after n_loc samples each: {u, u^2, grad[4]}, chain order (deterministic)
+void rgnn_block(DeviceBatch &b, const mat &W, int n_loc, int spu, double h, double out[6]) {
+    ck(mcrg_rgnn_set_weights(b.ctx, W.data()), "mcrg_rgnn_set_weights");
+    ck(mcrg_rgnn_accumulators_reset(b.ctx), "mcrg_rgnn_accumulators_reset");
+    ck(mcrg_rgnn_run(b.ctx, n_loc, spu, h), "mcrg_rgnn_run");
+    std::vector<double> s((size_t)b.replicas * 6);
+    ck(mcrg_rgnn_accumulators_get(b.ctx, s.data()), "mcrg_rgnn_accumulators_get");
+    for (int k = 0; k < 6; ++k) out[k] = 0.0;
+    for (int r = 0; r < b.replicas; ++r)
+        for (int k = 0; k < 6; ++k) out[k] += s[(size_t)r * 6 + k];
+}
+
+std::unique_ptr<DeviceBatch> equilibrated_batch(int L, int R, double K, int n_eq, int spu) {
+    std::unique_ptr<DeviceBatch> b(new DeviceBatch(L, R, mcrg_b200::take_batch_base(R)));
+    ck(mcrg_set_couplings(b->ctx, &K, 1), "mcrg_set_couplings");
+    ck(mcrg_init_hot(b->ctx), "mcrg_init_hot");
+    ck(mcrg_sweep(b->ctx, n_eq * spu), "mcrg_sweep");
+    return b;
+}
+}  // namespace
+
+void RenormalizationGroupNeuralNetwork::train_scalar_output(int L, int n_cycles, int n_samples, int n_samples_eq, double K,
+                                                            double h, double eta) {
+    // rgnn.cpp:46-190.  File name, header and row format as the reference writes them (rgnn.cpp:56-69, 154).
+    const std::string filename = "train_scalar_b" + std::to_string(b_) + "_L" + std::to_string(L) + "_K" + get_rounded_str(K, 7) + ".txt";
+    fptr_ = fopen(filename.c_str(), "w");
+    if (!fptr_) throw std::runtime_error("cannot open " + filename);
+    fprintf(fptr_, "# Initial Weights: ");
+    for (int i = 0; i < b_; ++i)
+        for (int j = 0; j < b_; ++j) fprintf(fptr_, "%20.10lf", W_(i, j));
+    fprintf(fptr_, "\n# Cycles, Avg Output L, Var Output L, Avg Output S, Var Output S, MSE, || MSE Gradient ||\n");
+
+    const int R = n_processes_, spu = settings().sweeps_per_update;
+    const int n_loc = (n_samples + R - 1) / R;
+    const double n_tot = (double)R * n_loc;
+    auto big = equilibrated_batch(L, R, K, n_samples_eq, spu);         // rgnn.cpp:88-89
+    auto small = equilibrated_batch(L / b_, R, K, n_samples_eq, spu);  // rgnn.cpp:92-94
+    double mse = 0.0;
+    for (int cycles = 0; cycles <= n_cycles; ++cycles) {
+        double sL[6], sS[6];
+        rgnn_block(*big, W_, n_loc, spu, h, sL);    // rgnn.cpp:106-130 for the large lattice ...
+        rgnn_block(*small, W_, n_loc, spu, h, sS);  // ... and the small one
+        const double uL_avg = sL[0] / n_tot, uS_avg = sS[0] / n_tot;
+        const double uL_var = sL[1] / n_tot - uL_avg * uL_avg, uS_var = sS[1] / n_tot - uS_avg * uS_avg;
+        mse = (uL_avg - uS_avg) * (uL_avg - uS_avg);  // rgnn.cpp:145
+        mat grad(b_, b_);
+        double gnorm = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            grad.data()[k] = 2 * (uL_avg - uS_avg) * (sL[2 + k] / n_tot - sS[2 + k] / n_tot);  // rgnn.cpp:146
+            gnorm += grad.data()[k] * grad.data()[k];
+        }
+        gnorm = std::sqrt(gnorm);
+        if (cycles % 100 == 0 && !settings().quiet) printf("%10i%15.7e%15.7e%15.7e%15.7e\n", cycles, uL_avg, uS_avg, mse, gnorm);
+        fprintf(fptr_, "%10i%15.7e%15.7e%15.7e%15.7e%15.7e%15.7e\n", cycles, uL_avg, uL_var, uS_avg, uS_var, mse, gnorm);
+        update_weights(eta, grad);  // rgnn.cpp:159
+    }
+    final_mse_ = mse;
+    fprintf(fptr_, "\n# Final Weights: ");
+    for (int i = 0; i < b_; ++i)
+        for (int j = 0; j < b_; ++j) fprintf(fptr_, "%20.10lf", W_(i, j));
+    // rgnn.cpp:172-188: one more configuration of the large lattice pushed through the filter, level by level
+    fprintf(fptr_, "\n# Example Flow: ");
+    ck(mcrg_sweep(big->ctx, spu), "mcrg_sweep");
+    imat spins(L, L);
+    ck(mcrg_get_spins_i32_colmajor(big->ctx, 0, 1, spins.data()), "mcrg_get_spins_i32_colmajor");
+    mat output = spins.cast<double>();
+    while (output.rows() > 1) {
+        for (int i = 0; i < output.rows(); ++i)
+            for (int j = 0; j < output.cols(); ++j) fprintf(fptr_, "%20.10lf", output(i, j));
+        fprintf(fptr_, ", ");
+        apply_filter(output);
+    }
+    fprintf(fptr_, "%20.10lf", output(0, 0));
+    fclose(fptr_);
+    fptr_ = NULL;
+}
+
+void RenormalizationGroupNeuralNetwork::test_scalar_output(int L, int n_samples, int n_samples_eq, double K0, double DeltaK) {
+    // rgnn.cpp:192-278
+    const std::string filename = "test_scalar_b" + std::to_string(b_) + "_L" + std::to_string(L) + "_K" + get_rounded_str(K0, 7) + ".txt";
+    fptr_ = fopen(filename.c_str(), "w");
+    if (!fptr_) throw std::runtime_error("cannot open " + filename);
+    fprintf(fptr_, "\n# Coupling K, Temperature T, Avg Output L, Var Output L, Avg Output S, Var Output S, MSE\n");
+    const int R = n_processes_, spu = settings().sweeps_per_update;
+    const int n_loc = (n_samples + R - 1) / R;
+    const double n_tot = (double)R * n_loc;
+    const double dK = DeltaK / 50;
+    for (double K = K0 - DeltaK; K <= K0 + DeltaK; K += dK) {
+        auto big = equilibrated_batch(L, R, K, n_samples_eq, spu);
+        auto small = equilibrated_batch(L / b_, R, K, n_samples_eq, spu);
+        double sL[6], sS[6];
+        rgnn_block(*big, W_, n_loc, spu, 1e-4, sL);
+        rgnn_block(*small, W_, n_loc, spu, 1e-4, sS);
+        const double T = -1.0 / K;
+        const double uL_avg = sL[0] / n_tot, uS_avg = sS[0] / n_tot;
+        const double uL_var = sL[1] / n_tot - uL_avg * uL_avg, uS_var = sS[1] / n_tot - uS_avg * uS_avg;
+        const double mse = (uL_avg - uS_avg) * (uL_avg - uS_avg);
+        if (!settings().quiet) printf("%15.7e%15.7e%15.7e%15.7e%15.7e\n", K, T, uL_avg, uS_avg, mse);
+        fprintf(fptr_, "%15.7e%15.7e%15.7e%15.7e%15.7e%15.7e%15.7e\n", K, T, uL_avg, uL_var, uS_avg, uS_var, mse);
+        fflush(fptr_);
+    }
+    fclose(fptr_);
+    fptr_ = NULL;
+}

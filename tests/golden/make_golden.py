@@ -132,6 +132,27 @@ def statistical():
     print("statistical.json written")
 
 
+def train_log_rows():
+    """Cycle-0 rows of the training logs checked into the reference repo (train_scalar_b2_L8_K*.txt:3): the weights
+    are the known W0 = [.5 -.5; .5 -.5] there (line 1), so the row pins <u_L>, Var u_L, <u_S>, Var u_S of the sampler +
+    RGNN forward pass at L = 8 / 4 for five couplings, from 1e4 samples each (train.cpp:8-10)."""
+    import glob
+
+    rows = []
+    for path in sorted(glob.glob("/root/reference/train_scalar_b2_L8_K*.txt")):
+        with open(path) as f:
+            lines = f.read().splitlines()
+        w0 = [float(x) for x in lines[0].split(":")[1].split()]
+        c0 = [float(x) for x in lines[2].split()]
+        assert c0[0] == 0
+        K = float(os.path.basename(path).split("_K")[1][:-4])
+        rows.append(dict(file=os.path.basename(path), K=K, W0=w0, n_samples=10000, uL=c0[1], varL=c0[2], uS=c0[3], varS=c0[4],
+                         mse=c0[5], grad_norm=c0[6]))
+    with open(os.path.join(HERE, "train_logs_cycle0.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    print("train_logs_cycle0.json:", len(rows), "rows")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--fast", action="store_true")
@@ -139,5 +160,7 @@ if __name__ == "__main__":
     if not _libs.ref_available():
         sys.exit("oracle/_ref/libmcrg_ref.so missing: run `make -C oracle ref` where /root/reference exists")
     deterministic()
+    train_log_rows()
     if not a.fast:
         statistical()
+

@@ -86,3 +86,55 @@ def test_reference_main_cpp_runs_unchanged(tmp_path):
         assert len(rows) == 6  # floor(log 128 / log 2) - 1 blocking levels
         lam = [float(r.split(",")[1]) for r in rows]
         assert all(1.7 < x < 2.3 for x in lam), lam
+
+
+def test_rgnn_cycle0_matches_reference_training_logs(tmp_path):
+    """Known answers from the reference's own checked-in logs (train_scalar_b2_L8_K*.txt:3, via
+    tests/golden/train_logs_cycle0.json): with W0 = [.5 -.5; .5 -.5], <u_L=8>, Var, <u_S=4>, Var at five couplings.
+    The logged row is a 1e4-sample average, so its statistical error is sqrt(Var/1e4) (inflated x1.5 for
+    autocorrelation); ours uses 4e6 samples.  3 sigma."""
+    with open(os.path.join(_libs.ROOT, "tests", "golden", "train_logs_cycle0.json")) as f:
+        rows = json.load(f)
+    assert len(rows) == 5
+    for row in rows:
+        d = tmp_path / f"K{row['K']}"
+        d.mkdir()
+        out = run([APP, "train", "8", repr(float(row["K"])), "0", "4000000", "2000"], d,
+                  {"MCRG_REPLICAS": "4096", "MCRG_SWEEPS_PER_UPDATE": "4", "MCRG_QUIET": "1"})
+        assert "RESULT final_mse" in out
+        log = (d / f"train_scalar_b2_L8_K{row['K']:.7g}.txt").read_text().splitlines()
+        assert log[0].startswith("# Initial Weights:") and [float(x) for x in log[0].split(":")[1].split()] == row["W0"]
+        assert log[1] == "# Cycles, Avg Output L, Var Output L, Avg Output S, Var Output S, MSE, || MSE Gradient ||"
+        c0 = [float(x) for x in log[2].split()]
+        assert re.fullmatch(r"\s+0(\s+-?\d\.\d{7}e[+-]\d\d){6}", log[2])
+        for got, want, var in ((c0[1], row["uL"], row["varL"]), (c0[3], row["uS"], row["varS"])):
+            assert abs(got - want) < 3 * 1.5 * np.sqrt(var / row["n_samples"]), (row["K"], got, want)
+        for got, want in ((c0[2], row["varL"]), (c0[4], row["varS"])):
+            assert abs(got - want) < 0.06 * want, (row["K"], got, want)  # variance of a variance: ~sqrt(2/1e4) x kurtosis
+        assert any(l.startswith("# Final Weights:") for l in log) and any(l.startswith("# Example Flow:") for l in log)
+
+
+def test_rgnn_training_reduces_the_cost(tmp_path):
+    """train.cpp's experiment in miniature: minimise (<u_L> - <u_{L/2}>)^2 with ADAM from W0; the cost must fall and
+    the weights keep the symmetry the reference's finished runs show (W00 = W10, W01 = W11: its Final Weights rows)."""
+    out = run([APP, "train", "8", repr(KC), "300", "20000", "1000"], tmp_path, {"MCRG_REPLICAS": "4096", "MCRG_QUIET": "1"})
+    m = re.search(r"RESULT final_mse (\S+) W (\S+) (\S+) (\S+) (\S+)", out)
+    mse, w00, w01, w10, w11 = [float(x) for x in m.groups()]
+    log = [l for l in (tmp_path / f"train_scalar_b2_L8_K{KC:.7g}.txt").read_text().splitlines() if l and not l.startswith("#")]
+    assert len(log) == 301
+    first, last = float(log[0].split()[5]), np.mean([float(l.split()[5]) for l in log[-20:]])
+    assert last < 0.5 * first, (first, last)
+    assert abs(w00 - w10) < 0.05 and abs(w01 - w11) < 0.05, (w00, w01, w10, w11)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BUILD, "ref_train")), reason="ref_train is built only where /root/reference exists")
+def test_reference_train_cpp_runs_unchanged(tmp_path):
+    """train.cpp:7-34 as shipped: 6 temperatures x 1e4 cycles x 1e4 samples at L = 8 (hours on the reference's cluster)."""
+    out = run([os.path.join(BUILD, "ref_train")], tmp_path, {"MCRG_REPLICAS": "2048", "MCRG_QUIET": "1"}, timeout=1500)
+    rows = [l.split() for l in out.splitlines() if re.fullmatch(r"\d\.\d+e[+-]\d+ \d\.\d+e[+-]\d+", l.strip())]
+    assert len(rows) == 6  # printf("%e %e\n", T, final_mse_), train.cpp:33
+    logs = sorted(p.name for p in tmp_path.glob("train_scalar_b2_L8_K*.txt"))
+    assert len(logs) == 6
+    for name in logs:
+        lines = (tmp_path / name).read_text().splitlines()
+        assert sum(1 for l in lines if l and not l.startswith("#")) == 10001

@@ -385,3 +385,55 @@ def test_products_beyond_int64(mc):
     assert a[lay.slot_ss + 0] == n * s0 * s0 and n * s0 * s0 > 2**63
     assert a[lay.slot_sbs + 0] == n * s1 * s0
     assert a[lay.slot_m2] == n * (L * L) ** 2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# RGNN forward pass and finite-difference gradient (rgnn.cpp:281-339)   (bit-exact against the oracle's order)
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("L", [2, 4, 8, 16, 64])
+def test_rgnn_eval_matches_oracle(mc, L):
+    o = _libs.oracle()
+    rng = np.random.default_rng(L)
+    R = 31  # not a multiple of the 14 replicas a block handles
+    spins = np.stack([_libs.random_lattice(L, 500 + r, p_up=0.5 + 0.3 * (r % 2)) for r in range(R)])
+    for W in (np.array([[0.5, -0.5], [0.5, -0.5]]), 0.3 * rng.standard_normal((2, 2))):  # train.cpp:19-23 and random
+        with mc.Context(L, R) as ctx:
+            ctx.set_spins(spins)
+            ctx.rgnn_set_weights(W)
+            u, g = ctx.rgnn_eval(1e-4)
+        Wcm = np.ascontiguousarray(W.T).ravel()  # column-major for the oracle
+        for r in range(R):
+            want = o.orc_rgnn_scalar_output(L, spins[r], 2, Wcm)
+            assert u[r] == want, (L, r, u[r], want)
+            gw = np.zeros(4)
+            o.orc_rgnn_gradient(L, spins[r], 2, Wcm.copy(), 1e-4, gw)
+            assert np.array_equal(g[r], gw.reshape(2, 2).T), (L, r)
+
+
+def test_rgnn_run_accumulates_like_the_reference_loop(mc):
+    """rgnn.cpp:106-123: update, then u, u^2 and the gradient of the new configuration are added up."""
+    o = _libs.oracle()
+    L, R, n, m, h, seed = 8, 5, 7, 2, 1e-4, 321
+    W = np.array([[0.5, -0.5], [0.5, -0.5]])
+    Wcm = np.ascontiguousarray(W.T).ravel()
+    with mc.Context(L, R, seed=seed) as ctx:
+        ctx.set_couplings([KC])
+        ctx.init_hot()
+        ctx.rgnn_set_weights(W)
+        ctx.rgnn_run(n, m, h)
+        sums = ctx.rgnn_sums()
+        ctx.rgnn_reset()
+        assert (ctx.rgnn_sums() == 0).all()
+    for r in range(R):
+        s = oracle_hot(L, seed, r)
+        want = np.zeros(6)
+        for k in range(n):
+            o.orc_metropolis(L, s, KC, seed, r, k * m, m)
+            u = o.orc_rgnn_scalar_output(L, s, 2, Wcm)
+            g = np.zeros(4)
+            o.orc_rgnn_gradient(L, s, 2, Wcm.copy(), h, g)
+            want[0] += u
+            want[1] += u * u
+            want[2:] += g
+        assert np.array_equal(sums[r], want), (r, sums[r], want)
