@@ -59,7 +59,8 @@ uint64_t mcrg_stream_handle(mcrg_ctx *ctx);
 int mcrg_timer_start(mcrg_ctx *ctx);
 int mcrg_timer_stop(mcrg_ctx *ctx, float *ms);
 int mcrg_levels_full(int L); /* floor(log L / log 2) - 1, mcrg.cpp:43 */
-/* tuning knobs: rows per strip of the sweep kernel (0 = heuristic), sweeps fused per launch, CUDA-graph use */
+/* tuning knobs: rows per strip of the sweep kernel (0 = heuristic; lattices up to 512^2 then use the resident kernel,
+ * a non-zero value forces the strip kernel), sweeps fused per launch, CUDA-graph use */
 int mcrg_set_tuning(mcrg_ctx *ctx, int strip_rows, int fuse_sweeps, int use_graphs);
 
 /* ---- state ---------------------------------------------------------------------------------------------- */

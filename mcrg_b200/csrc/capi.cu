@@ -59,6 +59,7 @@ struct mcrg_ctx {
     cudaEvent_t ev_meas[2] = {nullptr, nullptr}, ev_pyr[2] = {nullptr, nullptr};
     bool pyr_pending[2] = {false, false};
     int overlap = 1;      // run the pyramid on stream2
+    int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
     int last_parity = 0;  // which level-1 / popcount buffer the last measurement used
     size_t level1_words = 0, cnt_cells = 0;
     uint32_t *planes[2] = {nullptr, nullptr};
@@ -243,6 +244,35 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     if (probe) cudaEventRecord(probe[4], c->stream);
 }
 
+// an explicit strip height (mcrg_set_tuning / MCRG_STRIP_ROWS) asks for the strip kernel
+bool use_resident(const mcrg_ctx *c) { return c->resident && c->strip_rows == 0 && c->L <= RESIDENT_MAX_L; }
+
+void enqueue_resident(mcrg_ctx *c, bool measure, int n_samples, int m, int n_lv, int accumulate, int bin) {
+    ResidentArgs a;
+    a.planes = c->planes[c->cur];
+    a.T4 = c->T4;
+    a.T8 = c->T8;
+    a.anti = c->anti;
+    a.d_t = c->d_t;
+    a.t_off = 0;
+    a.seed = c->seed;
+    a.replica_base = c->replica_base;
+    a.L = c->L;
+    a.W = c->W;
+    a.bits = c->bits;
+    a.n_samples = n_samples;
+    a.m = m;
+    a.n_levels = n_lv;
+    a.accumulate = accumulate;
+    a.n_bins = c->n_bins;
+    a.bin = bin;
+    a.acc_lo = c->acc_lo;
+    a.acc_hi = c->acc_hi;
+    a.acc_d = c->acc_d;
+    a.S_out = c->S_out;
+    launch_resident(a, c->n_replicas, measure, c->stream);
+}
+
 int clamp_levels(const mcrg_ctx *c, int max_levels) {
     int n_lv = c->full_levels;
     if (max_levels >= 0 && max_levels < n_lv) n_lv = max_levels;
@@ -313,6 +343,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
         CK(cudaEventCreateWithFlags(&c->ev_pyr[p], cudaEventDisableTiming));
     }
     if (const char *e = getenv("MCRG_OVERLAP")) c->overlap = atoi(e);
+    if (const char *e = getenv("MCRG_RESIDENT")) c->resident = atoi(e);
     const size_t plane_words = (size_t)n_replicas * 2 * L * c->W;
     CK(cudaMalloc(&c->planes[0], plane_words * 4));
     CK(cudaMalloc(&c->planes[1], plane_words * 4));
@@ -554,7 +585,8 @@ int mcrg_sweep(mcrg_ctx *c, int n_sweeps) {
     if (n_sweeps < 0) return fail(MCRG_ERR_ARG, "n_sweeps=%d < 0", n_sweeps);
     if (n_sweeps == 0) return 0;
     CK(cudaSetDevice(c->device));
-    enqueue_sweeps(c, n_sweeps, 0);
+    if (use_resident(c)) enqueue_resident(c, false, 1, n_sweeps, 0, 0, 0);
+    else enqueue_sweeps(c, n_sweeps, 0);
     launch_advance_t(c->d_t, (unsigned long long)n_sweeps, c->stream);
     c->t_host += (unsigned long long)n_sweeps;
     CK(cudaGetLastError());
@@ -603,6 +635,15 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
     CK(cudaSetDevice(c->device));
     const int n_lv = clamp_levels(c, max_levels);
     const int m = sweeps_per_sample;
+    if (use_resident(c)) {  // small lattices: the whole block of samples is one launch
+        enqueue_resident(c, true, n_samples, m, n_lv, 1, bin);
+        if (m > 0) launch_advance_t(c->d_t, (unsigned long long)n_samples * m, c->stream);
+        c->t_host += (unsigned long long)n_samples * m;
+        c->last_levels = n_lv;
+        c->measured = false;  // the blocked lattices of a resident run never leave shared memory
+        CK(cudaGetLastError());
+        return 0;
+    }
     int done = 0;
     if (c->use_graphs) {
         const int chunk = 16;

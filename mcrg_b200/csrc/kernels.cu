@@ -300,6 +300,49 @@ __global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
         atomicAdd(&a.cnt[((size_t)r * (MAX_LEVELS + 1) + a.level) * 4 + threadIdx.x], (unsigned long long)red[threadIdx.x]);
 }
 
+// ---- pieces shared by k_tail and k_resident ---------------------------------------------------------------------
+
+// Levels start..n_levels of one replica, level `start` already in `cur` (natural layout): correlator popcounts of
+// every level into red[lv*4..], blocking to the next level ping-ponging between cur and nxt.  Optionally mirrors
+// every produced level to global memory.  All threads of the CTA call this; ends synchronised.
+__device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, int L, int start, int n_levels, unsigned int *red,
+                                                uint32_t *levels_out, const size_t *level_off, int r, uint64_t seed,
+                                                uint32_t replica, unsigned long long t) {
+    for (int lv = start; lv <= n_levels; ++lv) {
+        const int Ln = L >> lv, Wn = nat_words(Ln), lw = ilog2(Wn);
+        StripN s;
+        s.x = cur;
+        s.W = Wn;
+        s.bits = nat_bits(Ln);
+        s.mask = valid_mask(s.bits);
+        Counts c = {0u, 0u, 0u, 0u};
+        const int n = Ln << lw;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int lr = idx >> lw;
+            measure_rowN(s, lr, (lr + 1 == Ln) ? 0 : lr + 1, idx & (Wn - 1), c);
+        }
+        warp_reduce_to(c, red + lv * 4);
+        if (lv < n_levels) {
+            const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
+            uint32_t *glob = levels_out ? levels_out + level_off[lv + 1] + (size_t)r * Lb * Wb : nullptr;
+            const int nb = Lb << lwb;
+            for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
+                const int yb = idx >> lwb, wb = idx & (Wb - 1);
+                uint32_t maj, tie;
+                block_pairN(s, 2 * yb, wb, maj, tie);
+                uint32_t o = maj;
+                if (tie) o |= tie & tie_word(seed, (uint32_t)idx, replica, t, lv + 1);
+                nxt[idx] = o;
+                if (glob) glob[idx] = o;
+            }
+        }
+        __syncthreads();
+        uint32_t *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+}
+
 __device__ __forceinline__ void add128(unsigned long long *lo, long long *hi, __int128 v) {
     const unsigned long long vlo = (unsigned long long)v;
     const long long vhi = (long long)(v >> 64);
@@ -307,6 +350,40 @@ __device__ __forceinline__ void add128(unsigned long long *lo, long long *hi, __
     const unsigned long long nl = old + vlo;
     *lo = nl;
     *hi = *hi + vhi + (nl < old ? 1 : 0);
+}
+
+// The accumulator slots that are live for a pyramid of n_levels blocking levels, in a compact order:
+// k -> (slot index in the public layout, this sample's contribution).  S_sh[lv*4 + {nn, nnn, plaq, sum}].
+// mcrg.cpp:86-97 with the column-major flatten of definitions.cpp:9-19 (index b*NOP+a holds X_a * Y_b).
+__device__ __forceinline__ int acc_live_slots(int n_levels) { return 3 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels; }
+
+__device__ __forceinline__ void acc_slot_value(int k, int n_levels, const long long *S_sh, int &slot, __int128 &v) {
+    const long long M = S_sh[3];
+    if (k < 3) {
+        slot = k;  // SLOT_N, SLOT_ABSM, SLOT_M2
+        v = k == 0 ? (__int128)1 : (k == 1 ? (__int128)(M < 0 ? -M : M) : (__int128)M * M);
+        return;
+    }
+    k -= 3;
+    if (k < NOP * (n_levels + 1)) {
+        const int lv = k / NOP, op = k - lv * NOP;
+        slot = SLOT_S + lv * NOP + op;
+        v = S_sh[lv * 4 + op];
+        return;
+    }
+    k -= NOP * (n_levels + 1);
+    if (k < NOP * NOP * (n_levels + 1)) {
+        const int lv = k / (NOP * NOP), e = k - lv * NOP * NOP, b = e / NOP, al = e - b * NOP;
+        slot = SLOT_SS + lv * NOP * NOP + e;
+        v = (__int128)S_sh[lv * 4 + al] * S_sh[lv * 4 + b];
+        return;
+    }
+    k -= NOP * NOP * (n_levels + 1);
+    const bool vs_prev = k < NOP * NOP * n_levels;  // S(n) x S(n-1), then S(n) x S(0)
+    if (!vs_prev) k -= NOP * NOP * n_levels;
+    const int n1 = k / (NOP * NOP), e = k - n1 * NOP * NOP, b = e / NOP, al = e - b * NOP, n = n1 + 1;
+    slot = (vs_prev ? SLOT_SBS : SLOT_SB0) + n1 * NOP * NOP + e;
+    v = (__int128)S_sh[n * 4 + al] * S_sh[(vs_prev ? n - 1 : 0) * 4 + b];
 }
 
 __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
@@ -323,40 +400,7 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
         stage_rows(bufA, a.in + (size_t)r * Ln * Wn, 0, Ln, Wn, Ln);
     }
     __syncthreads();
-    uint32_t *cur = bufA, *nxt = bufB;
-    for (int lv = a.start; lv <= a.n_levels; ++lv) {
-        const int Ln = a.L >> lv, Wn = nat_words(Ln), lw = ilog2(Wn);
-        StripN s;
-        s.x = cur;
-        s.W = Wn;
-        s.bits = nat_bits(Ln);
-        s.mask = valid_mask(s.bits);
-        Counts c = {0u, 0u, 0u, 0u};
-        const int n = Ln << lw;
-        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            const int lr = idx >> lw;
-            measure_rowN(s, lr, (lr + 1 == Ln) ? 0 : lr + 1, idx & (Wn - 1), c);
-        }
-        warp_reduce_to(c, red + lv * 4);
-        if (lv < a.n_levels) {
-            const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
-            uint32_t *glob = a.levels_out + a.level_off[lv + 1] + (size_t)r * Lb * Wb;
-            const int nb = Lb << lwb;
-            for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-                const int yb = idx >> lwb, wb = idx & (Wb - 1);
-                uint32_t maj, tie;
-                block_pairN(s, 2 * yb, wb, maj, tie);
-                uint32_t o = maj;
-                if (tie) o |= tie & tie_word(a.seed, (uint32_t)idx, replica, t, lv + 1);
-                nxt[idx] = o;
-                glob[idx] = o;
-            }
-        }
-        __syncthreads();
-        uint32_t *tmp = cur;
-        cur = nxt;
-        nxt = tmp;
-    }
+    pyramid_in_smem(bufA, bufB, a.L, a.start, a.n_levels, red, a.levels_out, a.level_off, r, a.seed, replica, t);
     // raw popcounts -> the reference's sums; levels below `start` were counted by k_sweep0 / k_level
     if (threadIdx.x <= a.n_levels) {
         const int lv = threadIdx.x;
@@ -380,37 +424,137 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
     __syncthreads();
     if (!a.accumulate) return;
     const size_t base = ((size_t)r * a.n_bins + a.bin) * N_SLOTS;
-    const long long M = S_sh[3];
-    for (int slot = threadIdx.x; slot < N_SLOTS; slot += blockDim.x) {
-        __int128 v = 0;
-        bool live = true;
-        if (slot == SLOT_N) v = 1;
-        else if (slot == SLOT_ABSM) v = M < 0 ? -M : M;
-        else if (slot == SLOT_M2) v = (__int128)M * M;
-        else if (slot < SLOT_SS) {
-            const int k = slot - SLOT_S, lv = k / NOP, op = k - lv * NOP;
-            live = lv <= a.n_levels;
-            if (live) v = S_sh[lv * 4 + op];
-        } else if (slot < SLOT_SBS) {
-            const int k = slot - SLOT_SS, lv = k / (NOP * NOP), e = k - lv * NOP * NOP, b = e / NOP, al = e - b * NOP;
-            live = lv <= a.n_levels;
-            if (live) v = (__int128)S_sh[lv * 4 + al] * S_sh[lv * 4 + b];
-        } else if (slot < SLOT_SB0) {
-            const int k = slot - SLOT_SBS, n1 = k / (NOP * NOP), e = k - n1 * NOP * NOP, b = e / NOP, al = e - b * NOP;
-            const int n = n1 + 1;
-            live = n <= a.n_levels;
-            if (live) v = (__int128)S_sh[n * 4 + al] * S_sh[(n - 1) * 4 + b];  // flatten: index b*NOP+a holds Sb_a*S_b
-        } else {
-            const int k = slot - SLOT_SB0, n1 = k / (NOP * NOP), e = k - n1 * NOP * NOP, b = e / NOP, al = e - b * NOP;
-            const int n = n1 + 1;
-            live = n <= a.n_levels;
-            if (live) v = (__int128)S_sh[n * 4 + al] * S_sh[b];  // blocked level n against level 0
-        }
-        if (live) add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], v);
+    const int n_live = acc_live_slots(a.n_levels);
+    for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
+        int slot;
+        __int128 v;
+        acc_slot_value(k, a.n_levels, S_sh, slot, v);
+        add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], v);
     }
     if (threadIdx.x == 0) {
-        const double m = (double)M;
+        const double m = (double)S_sh[3];
         a.acc_d[((size_t)r * a.n_bins + a.bin) * N_DSLOTS + 0] += m * m * m * m;
+    }
+}
+
+// ---- resident kernel: a whole replica (L <= RESIDENT_MAX_L) lives in one CTA's shared memory -------------------------
+// One launch = n_samples x { [measure level 0 + block, pyramid in shared memory, accumulate], m Metropolis sweeps }.
+// Local row lr holds global row y = lr-1; rows 0 and L+1 are periodic halo copies, refreshed after every half-sweep
+// (2W words) instead of recomputed.  Global memory is touched at the start (load), at the end (store, accumulator
+// flush) and nowhere in between; the accumulators of the launch live in shared memory as exact 128-bit sums.
+template <bool MEASURE>
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_resident(const ResidentArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
+    __shared__ long long S_sh[(MAX_LEVELS + 1) * 4];
+    __shared__ __align__(16) McTable tab;
+    const int r = blockIdx.x;
+    const int L = a.L, W = a.W, lw = ilog2(W);
+    const int rows = L + 2;
+    const uint32_t replica = a.replica_base + (uint32_t)r;
+    const unsigned long long t0 = *a.d_t + a.t_off;
+    Strip0 s;
+    s.base = smem;
+    s.rows = rows;
+    s.W = W;
+    s.bits = a.bits;
+    s.mask = valid_mask(a.bits);
+    s.L = L;
+    s.y_first = L - 1;
+    const ResidentLayout lay = resident_layout(L, blockDim.x, a.n_levels);
+    McQueue q;
+    q.ent = smem + lay.queue_off;
+    q.cap = lay.cap;
+    uint32_t *bufA = smem + lay.bufA_off, *bufB = smem + lay.bufB_off;
+    unsigned long long *acc_lo = reinterpret_cast<unsigned long long *>(smem + lay.acc_off);
+    const int n_live = acc_live_slots(a.n_levels);
+    long long *acc_hi = reinterpret_cast<long long *>(acc_lo + n_live);
+
+    uint32_t *gl = a.planes + (size_t)r * 2 * L * W;
+    stage_rows(s0_plane(s, 0), gl, s.y_first, rows, W, L);
+    stage_rows(s0_plane(s, 1), gl + (size_t)L * W, s.y_first, rows, W, L);
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        const uint32_t T = (k & 1) ? a.T8[r] : a.T4[r];
+        tab.tm[k >> 1][k & 1] = ((T >> (31 - (k >> 1))) & 1u) ? 0xFFFFFFFFu : 0u;
+    }
+    if (MEASURE)
+        for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
+            acc_lo[k] = 0ull;
+            acc_hi[k] = 0ll;
+        }
+    const uint32_t anti = a.anti[r];
+    double m4 = 0.0;
+    __syncthreads();
+
+    for (int smp = 0; smp < a.n_samples; ++smp) {
+        const unsigned long long t = t0 + (unsigned long long)smp * a.m;
+        if (MEASURE) {
+            for (int k = threadIdx.x; k < (MAX_LEVELS + 1) * 4; k += blockDim.x) red[k] = 0;
+            __syncthreads();
+            Counts c = {0u, 0u, 0u, 0u};
+            const int npairs = (L >> 1) << lw;
+            for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
+                const int i = idx >> lw, w = idx & (W - 1);
+                uint32_t maj, tie;
+                measure_pair0(s, 1 + 2 * i, w, c, maj, tie);
+                uint32_t out = maj;
+                if (tie) out |= tie & tie_word(a.seed, (uint32_t)idx, replica, t, 1);
+                bufA[idx] = out;
+            }
+            warp_reduce_to(c, red);
+            __syncthreads();
+            pyramid_in_smem(bufA, bufB, L, 1, a.n_levels, red, nullptr, nullptr, r, a.seed, replica, t);
+            if (threadIdx.x <= a.n_levels) {
+                const int lv = threadIdx.x;
+                long long S[4];
+                counts_to_S((long long)(L >> lv), red[lv * 4 + 0], red[lv * 4 + 1], red[lv * 4 + 2], red[lv * 4 + 3], S);
+                for (int k = 0; k < 4; ++k) S_sh[lv * 4 + k] = S[k];
+            }
+            __syncthreads();
+            if (a.accumulate) {
+                for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
+                    int slot;
+                    __int128 v;
+                    acc_slot_value(k, a.n_levels, S_sh, slot, v);
+                    add128(&acc_lo[k], &acc_hi[k], v);
+                }
+                if (threadIdx.x == 0) {
+                    const double m = (double)S_sh[3];
+                    m4 += m * m * m * m;
+                }
+            }
+            // S_sh / red are rewritten only after the barriers inside the sweeps below (or at the loop top)
+        }
+        for (int h = 0; h < 2 * a.m; ++h) {
+            const int c = h & 1;
+            mc_half_sweep(s, c, 1, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
+            uint32_t *pc = s0_plane(s, c);  // refresh this colour's periodic halo rows
+            for (int w = threadIdx.x; w < 2 * W; w += blockDim.x) {
+                if (w < W) pc[w] = pc[L * W + w];
+                else pc[(L + 1) * W + (w - W)] = pc[W + (w - W)];
+            }
+            __syncthreads();
+        }
+    }
+
+    if (a.m > 0) {
+        unstage_rows(gl, s0_plane(s, 0) + W, 0, L, W, L);
+        unstage_rows(gl + (size_t)L * W, s0_plane(s, 1) + W, 0, L, W, L);
+    }
+    if (MEASURE) {
+        __syncthreads();
+        if (threadIdx.x <= a.n_levels)
+            for (int k = 0; k < 4; ++k) a.S_out[((size_t)r * (MAX_LEVELS + 1) + threadIdx.x) * 4 + k] = S_sh[threadIdx.x * 4 + k];
+        if (a.accumulate) {
+            const size_t base = ((size_t)r * a.n_bins + a.bin) * N_SLOTS;
+            for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
+                int slot;
+                __int128 v;
+                acc_slot_value(k, a.n_levels, S_sh, slot, v);  // only for the slot index
+                add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], ((__int128)acc_hi[k] << 64) | (__int128)acc_lo[k]);
+            }
+            if (threadIdx.x == 0) a.acc_d[((size_t)r * a.n_bins + a.bin) * N_DSLOTS + 0] += m4;
+        }
     }
 }
 
@@ -624,12 +768,22 @@ int sweep0_max_smem() {
         cudaError_t e1 = cudaFuncSetAttribute(k_sweep0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaError_t e2 = cudaFuncSetAttribute(k_sweep0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaError_t e3 = cudaFuncSetAttribute(k_level, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaFuncSetAttribute(k_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaFuncSetAttribute(k_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         g_max_smem = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) ? dyn : 48 * 1024;
         (void)cudaGetLastError();  // a refused opt-in only lowers the limit we plan with
     }
     return g_max_smem;
 }
 
+
+void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st) {
+    sweep0_max_smem();
+    const int threads = sweep0_threads(a.L, a.L - 2, 2);  // (L+2) rows of W words
+    const size_t smem = (size_t)resident_layout(a.L, threads, a.n_levels).total_words * sizeof(uint32_t);
+    if (measure) k_resident<true><<<n_replicas, threads, smem, st>>>(a);
+    else k_resident<false><<<n_replicas, threads, smem, st>>>(a);
+}
 
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st) {
     sweep0_max_smem();

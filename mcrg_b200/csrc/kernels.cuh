@@ -75,6 +75,43 @@ struct TailArgs {
     int accumulate;
 };
 
+constexpr int RESIDENT_MAX_L = 512;  // a replica up to this size (plus its pyramid) lives in one CTA's shared memory
+
+struct ResidentArgs {
+    uint32_t *planes;          // [replica][colour][y][w], updated in place
+    const uint32_t *T4, *T8, *anti;
+    const unsigned long long *d_t;
+    unsigned long long t_off;
+    uint64_t seed;
+    uint32_t replica_base;
+    int L, W, bits;
+    int n_samples, m;          // n_samples x { [measure], m sweeps }
+    int n_levels, accumulate, n_bins, bin;
+    unsigned long long *acc_lo;
+    long long *acc_hi;
+    double *acc_d;
+    long long *S_out;
+};
+
+// shared-memory carve-up of k_resident, in 32-bit words: planes | queue | bufA | bufB | 128-bit accumulators
+struct ResidentLayout {
+    int queue_off, bufA_off, bufB_off, acc_off, total_words, cap;
+};
+MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
+    ResidentLayout o;
+    const int W = l0_words(L), words = (L + 2) * W, warps = threads / 32;
+    o.cap = sweep0_queue_cap(words, warps);
+    o.queue_off = (2 * words + 3) & ~3;
+    o.bufA_off = (o.queue_off + 3 * o.cap * warps + 3) & ~3;
+    const int L1 = L / 2 > 0 ? L / 2 : 1, L2 = L / 4 > 0 ? L / 4 : 1;
+    o.bufB_off = (o.bufA_off + L1 * nat_words(L1) + 3) & ~3;
+    o.acc_off = (o.bufB_off + L2 * nat_words(L2) + 3) & ~3;
+    const int n_live = 3 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels;
+    o.total_words = o.acc_off + 4 * n_live;
+    return o;
+}
+
+void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st);
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st);
 void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st);
 void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st);
