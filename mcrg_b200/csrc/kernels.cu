@@ -155,10 +155,11 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
             else n1 = shift_down_index(n0, plane_o[off + d_dn], s.bits, s.mask);
             const uint32_t a1 = t ^ u ^ anti, a2 = t ^ d ^ anti, a3 = t ^ n0 ^ anti, a4 = t ^ n1 ^ anti;
             const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
-            const uint32_t ge2 = c12 | c34 | (x12 & x34);
+            // lanes with A >= 2 flip unconditionally; fold them in now so that only one word stays live
+            const uint32_t t2 = t ^ ((c12 | c34 | (x12 & x34)) & s.mask);
             sel = (x12 ^ x34) & ~(c12 | c34) & s.mask;   // A == 1
             eq = (sel | ~(a1 | a2 | a3 | a4)) & s.mask;  // A == 1 or A == 0: lanes that need a random number
-            uint32_t lt = 0;
+            uint32_t lt = 0;                             // subset of the initial eq, hence disjoint from the A >= 2 lanes
             if (eq) {
                 const uint32_t word_id = wid_base + ((uint32_t)y << lw);
                 const U4 r0 = mc_philox(seed, word_id, replica, t_lo, c3_base, 0);
@@ -166,7 +167,7 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
                 mc_compare4(r0, tab, 0, sel, eq, lt);
                 mc_compare4(r1, tab, 4, sel, eq, lt);
             }
-            plane_c[off] = t ^ ((ge2 | lt) & s.mask);
+            plane_c[off] = t2 ^ lt;
         }
         const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);  // ~10 % of the words
         if (eq != 0u) {
