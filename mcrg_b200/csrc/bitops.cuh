@@ -142,10 +142,31 @@ MCRG_HD uint32_t compress_even(uint32_t v) {
     return v;
 }
 
-// tie coin for 32 blocks of output word q (= yb*Wb + wb) of the level-`level` lattice
-MCRG_HD uint32_t tie_word(uint64_t seed, uint32_t q, uint32_t replica, uint64_t t, int level) {
-    return philox_keyed(seed, q, replica, t, PURPOSE_TIE, level).x;
+// Tie coins.  The 32 coins of output word q (= yb*Wb + wb) of the level-`level` lattice are ONE of the four output
+// words of a Philox call: call index = q with bits 8-9 removed, element = bits 8-9 of q.  A thread that walks its words
+// with stride 256 (every kernel here does, with 256 threads) therefore needs one call per four words; TieCache keeps
+// the last call.  The mapping is a fixed function of q, so results do not depend on who computes it.
+MCRG_HD uint32_t tie_group(uint32_t q) { return ((q >> 10) << 8) | (q & 255u); }
+MCRG_HD uint32_t tie_pick(const U4 &r, uint32_t q) {
+    const uint32_t e = (q >> 8) & 3u;
+    return e == 0u ? r.x : (e == 1u ? r.y : (e == 2u ? r.z : r.w));
 }
+MCRG_HD uint32_t tie_word(uint64_t seed, uint32_t q, uint32_t replica, uint64_t t, int level) {
+    return tie_pick(philox_keyed(seed, tie_group(q), replica, t, PURPOSE_TIE, level), q);
+}
+struct TieCache {
+    uint32_t group;
+    U4 r;
+    MCRG_HD void init() { group = 0xFFFFFFFFu; r.x = r.y = r.z = r.w = 0u; }
+    MCRG_HD uint32_t get(uint64_t seed, uint32_t q, uint32_t replica, uint64_t t, int level) {
+        const uint32_t g = tie_group(q);
+        if (g != group) {
+            r = philox_keyed(seed, g, replica, t, PURPOSE_TIE, level);
+            group = g;
+        }
+        return tie_pick(r, q);
+    }
+};
 
 // geometry helpers
 MCRG_HD int l0_words(int L) { return L >= 64 ? L / 64 : 1; }

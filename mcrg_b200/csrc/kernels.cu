@@ -229,13 +229,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
         Counts c = {0u, 0u, 0u, 0u};
         const int npairs = (a.R >> 1) << lw;
         uint32_t *lev1 = a.level1 + (size_t)r * (L >> 1) * W;
+        TieCache coins;
+        coins.init();
         for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
             const int i = idx >> lw, w = idx & (W - 1);
             uint32_t maj, tie;
             measure_pair0(s, a.H + 2 * i, w, c, maj, tie);
             const uint32_t q = (uint32_t)(((y0 >> 1) + i) << lw) + (uint32_t)w;
             uint32_t out = maj;
-            if (tie) out |= tie & tie_word(a.seed, q, replica, t, 1);
+            if (tie) out |= tie & coins.get(a.seed, q, replica, t, 1);
             lev1[q] = out;
         }
         warp_reduce_to(c, red);
@@ -285,13 +287,15 @@ __global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
         const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
         uint32_t *out_r = a.out + (size_t)r * Lb * Wb;
         const int nb = (a.R >> 1) << lwb;
+        TieCache coins;
+        coins.init();
         for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
             const int i = idx >> lwb, wb = idx & (Wb - 1);
             uint32_t maj, tie;
             block_pairN(s, 2 * i, wb, maj, tie);
             const uint32_t q = (uint32_t)(((y0 >> 1) + i) << lwb) + (uint32_t)wb;
             uint32_t o = maj;
-            if (tie) o |= tie & tie_word(a.seed, q, replica, t, a.level + 1);
+            if (tie) o |= tie & coins.get(a.seed, q, replica, t, a.level + 1);
             out_r[q] = o;
         }
     }
@@ -327,12 +331,14 @@ __device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, in
             const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
             uint32_t *glob = levels_out ? levels_out + level_off[lv + 1] + (size_t)r * Lb * Wb : nullptr;
             const int nb = Lb << lwb;
+            TieCache coins;
+            coins.init();
             for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
                 const int yb = idx >> lwb, wb = idx & (Wb - 1);
                 uint32_t maj, tie;
                 block_pairN(s, 2 * yb, wb, maj, tie);
                 uint32_t o = maj;
-                if (tie) o |= tie & tie_word(seed, (uint32_t)idx, replica, t, lv + 1);
+                if (tie) o |= tie & coins.get(seed, (uint32_t)idx, replica, t, lv + 1);
                 nxt[idx] = o;
                 if (glob) glob[idx] = o;
             }
@@ -494,12 +500,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_resident(const ResidentArg
             __syncthreads();
             Counts c = {0u, 0u, 0u, 0u};
             const int npairs = (L >> 1) << lw;
+            TieCache coins;
+            coins.init();
             for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
                 const int i = idx >> lw, w = idx & (W - 1);
                 uint32_t maj, tie;
                 measure_pair0(s, 1 + 2 * i, w, c, maj, tie);
                 uint32_t out = maj;
-                if (tie) out |= tie & tie_word(a.seed, (uint32_t)idx, replica, t, 1);
+                if (tie) out |= tie & coins.get(a.seed, (uint32_t)idx, replica, t, 1);
                 bufA[idx] = out;
             }
             warp_reduce_to(c, red);

@@ -146,12 +146,14 @@ void orc_block_spin_supplied(int N, int b, const int32_t *spins, const int32_t *
 }
 
 int32_t orc_tie_spin(uint64_t seed, uint32_t replica, uint64_t t, int level, int Nb, int ib, int jb) {
-    /* natural packed layout of the output lattice: row = jb, bit = ib, Wb words of 32 bits per row */
+    /* natural packed layout of the output lattice: row = jb, bit = ib, Wb words of 32 bits per row; the 32 coins of
+     * word q = jb*Wb + ib/32 are element (q>>8)&3 of the Philox call whose counter word is q with bits 8-9 removed */
     int Wb = Nb >= 32 ? Nb / 32 : 1;
     uint32_t q = (uint32_t)jb * (uint32_t)Wb + ((uint32_t)ib >> 5);
+    uint32_t group = ((q >> 10) << 8) | (q & 255u);
     uint32_t r[4];
-    orc_philox_keyed(seed, q, replica, t, ORC_PURPOSE_TIE, level, r);
-    return ((r[0] >> (ib & 31)) & 1u) ? 1 : -1;
+    orc_philox_keyed(seed, group, replica, t, ORC_PURPOSE_TIE, level, r);
+    return ((r[(q >> 8) & 3u] >> (ib & 31)) & 1u) ? 1 : -1;
 }
 
 void orc_block_spin_philox(int N, const int32_t *spins, uint64_t seed, uint32_t replica, uint64_t t, int level,
