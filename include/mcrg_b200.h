@@ -63,6 +63,16 @@ int mcrg_levels_full(int L); /* floor(log L / log 2) - 1, mcrg.cpp:43 */
  * a non-zero value forces the strip kernel), sweeps fused per launch, CUDA-graph use */
 int mcrg_set_tuning(mcrg_ctx *ctx, int strip_rows, int fuse_sweeps, int use_graphs);
 
+/* Which Markov-chain update mcrg_sweep / mcrg_run / mcrg_rgnn_run apply (one sweep-counter tick each):
+ *   MCRG_UPDATE_METROPOLIS  one full checkerboard Metropolis sweep (default; the north-star hot path);
+ *   MCRG_UPDATE_CLUSTER     one Swendsen-Wang cluster update: bonds between equal neighbours are activated with
+ *                           probability 1 - exp(-2|K|) — the add probability of IsingModel::IsingModel, ising.cpp:9 —
+ *                           and every cluster flips with probability 1/2.  Same family and same stationary distribution
+ *                           as the reference's Wolff update (grow_cluster, ising.cpp:96-149); no critical slowing down.
+ * Selecting the cluster update allocates 4 bytes per site for the union-find forest. */
+enum { MCRG_UPDATE_METROPOLIS = 0, MCRG_UPDATE_CLUSTER = 1 };
+int mcrg_set_update(mcrg_ctx *ctx, int mode);
+
 /* ---- state ---------------------------------------------------------------------------------------------- */
 /* IsingModel(K) (ising.cpp:3-11): n = 1 (all replicas) or n = n_replicas.  K < 0 is ferromagnetic. */
 int mcrg_set_couplings(mcrg_ctx *ctx, const double *K, int n);

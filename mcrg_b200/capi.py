@@ -48,6 +48,7 @@ def lib():
         l.mcrg_timer_stop.argtypes = [vp, P(C.c_float)]
         l.mcrg_levels_full.argtypes = [C.c_int]
         l.mcrg_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        l.mcrg_set_update.argtypes = [vp, C.c_int]
         l.mcrg_set_couplings.argtypes = [vp, vp, C.c_int]
         l.mcrg_init_hot.argtypes = [vp]
         l.mcrg_init_cold.argtypes = [vp]
@@ -144,6 +145,10 @@ class Context:
 
     def set_tuning(self, strip_rows=0, fuse_sweeps=1, use_graphs=1):
         _check(lib().mcrg_set_tuning(self._h, strip_rows, fuse_sweeps, use_graphs))
+
+    def set_update(self, mode):
+        """'metropolis' (default) or 'cluster' (Swendsen-Wang); applies to sweep(), run() and rgnn_run()."""
+        _check(lib().mcrg_set_update(self._h, {"metropolis": 0, "cluster": 1}[mode]))
 
     def set_couplings(self, K):
         K = np.ascontiguousarray(np.atleast_1d(np.asarray(K, np.float64)))

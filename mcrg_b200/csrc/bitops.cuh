@@ -22,7 +22,7 @@
 
 namespace mcrg {
 
-enum : int { PURPOSE_MC = 1, PURPOSE_TIE = 2, PURPOSE_INIT = 3 };
+enum : int { PURPOSE_MC = 1, PURPOSE_TIE = 2, PURPOSE_INIT = 3, PURPOSE_SW_BOND = 4, PURPOSE_SW_FLIP = 5 };
 
 struct U4 {
     uint32_t x, y, z, w;

@@ -41,9 +41,9 @@ int ilog2h(int v) {
 }
 
 struct GraphKey {
-    int m, n_lv, bin, chunk, cur, R, fuse;
+    int m, n_lv, bin, chunk, cur, R, fuse, mode;
     bool operator<(const GraphKey &o) const {
-        return std::tie(m, n_lv, bin, chunk, cur, R, fuse) < std::tie(o.m, o.n_lv, o.bin, o.chunk, o.cur, o.R, o.fuse);
+        return std::tie(m, n_lv, bin, chunk, cur, R, fuse, mode) < std::tie(o.m, o.n_lv, o.bin, o.chunk, o.cur, o.R, o.fuse, o.mode);
     }
 };
 
@@ -72,7 +72,9 @@ struct mcrg_ctx {
     unsigned long long *acc_lo = nullptr;
     long long *acc_hi = nullptr;
     double *acc_d = nullptr;
-    uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr;
+    uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr, *TP = nullptr;
+    int update_mode = MCRG_UPDATE_METROPOLIS;
+    int *sw_parent = nullptr;  // union-find forest of the cluster update, allocated by mcrg_set_update
     unsigned long long *d_t = nullptr;
     unsigned long long t_host = 0;
     double *rgnn_W = nullptr, *rgnn_acc = nullptr, *rgnn_u = nullptr, *rgnn_grad = nullptr;
@@ -162,6 +164,31 @@ void enqueue_sweeps(mcrg_ctx *c, int n, unsigned long long t_off) {
     }
 }
 
+// one Swendsen-Wang cluster update per sweep-counter tick, in place on the current buffer
+void enqueue_cluster_updates(mcrg_ctx *c, int n, unsigned long long t_off) {
+    SwArgs a;
+    a.planes = c->planes[c->cur];
+    a.parent = c->sw_parent;
+    a.TP = c->TP;
+    a.anti = c->anti;
+    a.d_t = c->d_t;
+    a.seed = c->seed;
+    a.replica_base = c->replica_base;
+    a.L = c->L;
+    a.W = c->W;
+    a.bits = c->bits;
+    for (int k = 0; k < n; ++k) {
+        a.t_off = t_off + (unsigned long long)k;
+        launch_sw_update(a, c->n_replicas, c->stream);
+    }
+}
+
+// n updates of the configured kind (mcrg_set_update)
+void enqueue_updates(mcrg_ctx *c, int n, unsigned long long t_off) {
+    if (c->update_mode == MCRG_UPDATE_CLUSTER) enqueue_cluster_updates(c, n, t_off);
+    else enqueue_sweeps(c, n, t_off);
+}
+
 // make the main stream wait for every pyramid still in flight on stream2 (no-op when nothing is pending)
 void join_pyramids(mcrg_ctx *c) {
     for (int p = 0; p < 2; ++p)
@@ -183,7 +210,8 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
         cudaStreamWaitEvent(c->stream, c->ev_pyr[parity], 0);
         c->pyr_pending[parity] = false;
     }
-    const int first = m > 0 ? 1 : 0;
+    const bool cluster = c->update_mode == MCRG_UPDATE_CLUSTER;
+    const int first = (m > 0 && !cluster) ? 1 : 0;  // a Metropolis sweep is fused into the measuring kernel
     const int R = choose_R(c, 2);
     SweepArgs a = sweep_args(c, R, first, t_off, parity);
     if (probe) cudaEventRecord(probe[0], c->stream);
@@ -240,12 +268,15 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     c->last_levels = n_lv;
     c->last_parity = parity;
     c->measured = true;
-    if (m > 1) enqueue_sweeps(c, m - 1, t_off + 1);
+    if (cluster) enqueue_cluster_updates(c, m, t_off);
+    else if (m > 1) enqueue_sweeps(c, m - 1, t_off + 1);
     if (probe) cudaEventRecord(probe[4], c->stream);
 }
 
 // an explicit strip height (mcrg_set_tuning / MCRG_STRIP_ROWS) asks for the strip kernel
-bool use_resident(const mcrg_ctx *c) { return c->resident && c->strip_rows == 0 && c->L <= RESIDENT_MAX_L; }
+bool use_resident(const mcrg_ctx *c) {
+    return c->resident && c->strip_rows == 0 && c->L <= RESIDENT_MAX_L && c->update_mode == MCRG_UPDATE_METROPOLIS;
+}
 
 void enqueue_resident(mcrg_ctx *c, bool measure, int n_samples, int m, int n_lv, int accumulate, int bin) {
     ResidentArgs a;
@@ -372,6 +403,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     CK(cudaMalloc(&c->T4, n_replicas * 4));
     CK(cudaMalloc(&c->T8, n_replicas * 4));
     CK(cudaMalloc(&c->anti, n_replicas * 4));
+    CK(cudaMalloc(&c->TP, n_replicas * 4));
     CK(cudaMalloc(&c->rgnn_W, 4 * sizeof(double)));
     CK(cudaMalloc(&c->rgnn_acc, (size_t)n_replicas * 6 * sizeof(double)));
     CK(cudaMalloc(&c->rgnn_u, (size_t)n_replicas * sizeof(double)));
@@ -409,6 +441,8 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->T4);
     cudaFree(c->T8);
     cudaFree(c->anti);
+    cudaFree(c->TP);
+    cudaFree(c->sw_parent);
     cudaFree(c->d_t);
     cudaFree(c->rgnn_W);
     cudaFree(c->rgnn_acc);
@@ -464,11 +498,21 @@ int mcrg_set_tuning(mcrg_ctx *c, int strip_rows, int fuse_sweeps, int use_graphs
     return 0;
 }
 
+int mcrg_set_update(mcrg_ctx *c, int mode) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (mode != MCRG_UPDATE_METROPOLIS && mode != MCRG_UPDATE_CLUSTER) return fail(MCRG_ERR_ARG, "unknown update mode %d", mode);
+    CK(cudaSetDevice(c->device));
+    if (mode == MCRG_UPDATE_CLUSTER && !c->sw_parent)
+        CK(cudaMalloc(&c->sw_parent, (size_t)c->n_replicas * c->L * c->L * sizeof(int)));
+    c->update_mode = mode;
+    return 0;
+}
+
 int mcrg_set_couplings(mcrg_ctx *c, const double *K, int n) {
     if (!c || !K) return fail(MCRG_ERR_ARG, "null pointer");
     if (n != 1 && n != c->n_replicas) return fail(MCRG_ERR_ARG, "n=%d must be 1 or n_replicas=%d", n, c->n_replicas);
     CK(cudaSetDevice(c->device));
-    std::vector<uint32_t> t4(c->n_replicas), t8(c->n_replicas), an(c->n_replicas);
+    std::vector<uint32_t> t4(c->n_replicas), t8(c->n_replicas), an(c->n_replicas), tp(c->n_replicas);
     for (int r = 0; r < c->n_replicas; ++r) {
         const double k = K[n == 1 ? 0 : r];
         if (!std::isfinite(k)) return fail(MCRG_ERR_ARG, "coupling %d is not finite", r);
@@ -480,11 +524,16 @@ int mcrg_set_couplings(mcrg_ctx *c, const double *K, int n) {
         t4[r] = (uint32_t)p4;
         t8[r] = (uint32_t)p8;
         an[r] = k > 0.0 ? 0xFFFFFFFFu : 0u;
+        // cluster update: bond probability 1 - exp(-2|K|) (ising.cpp:9), same fixed-point convention
+        double pb = std::floor((1.0 - std::exp(-2.0 * std::fabs(k))) * 4294967296.0);
+        if (pb > 4294967295.0) pb = 4294967295.0;
+        tp[r] = (uint32_t)pb;
     }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(c->T4, t4.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->T8, t8.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->anti, an.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->TP, tp.data(), c->n_replicas * 4, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -586,7 +635,7 @@ int mcrg_sweep(mcrg_ctx *c, int n_sweeps) {
     if (n_sweeps == 0) return 0;
     CK(cudaSetDevice(c->device));
     if (use_resident(c)) enqueue_resident(c, false, 1, n_sweeps, 0, 0, 0);
-    else enqueue_sweeps(c, n_sweeps, 0);
+    else enqueue_updates(c, n_sweeps, 0);
     launch_advance_t(c->d_t, (unsigned long long)n_sweeps, c->stream);
     c->t_host += (unsigned long long)n_sweeps;
     CK(cudaGetLastError());
@@ -648,7 +697,7 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
     if (c->use_graphs) {
         const int chunk = 16;
         while (n_samples - done >= chunk) {
-            GraphKey key{m, n_lv, bin, chunk, c->cur, c->strip_rows, c->fuse_sweeps};
+            GraphKey key{m, n_lv, bin, chunk, c->cur, c->strip_rows, c->fuse_sweeps, c->update_mode};
             auto it = c->graphs.find(key);
             const int cur_before = c->cur;
             if (it == c->graphs.end()) {
@@ -675,6 +724,7 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
                 // replay flips the ping-pong index as often as the capture did
                 int flips_per_sample = m > 0 ? 1 : 0;
                 if (m > 1) flips_per_sample += (m - 1 + c->fuse_sweeps - 1) / c->fuse_sweeps;
+                if (c->update_mode == MCRG_UPDATE_CLUSTER) flips_per_sample = 0;  // cluster updates work in place
                 if ((chunk * flips_per_sample) & 1) c->cur ^= 1;
                 c->last_levels = n_lv;
                 c->last_parity = (chunk - 1) & 1;
@@ -750,7 +800,7 @@ int mcrg_rgnn_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, double h) {
     if (!(h > 0.0)) return fail(MCRG_ERR_ARG, "h must be positive");
     CK(cudaSetDevice(c->device));
     for (int s = 0; s < n_samples; ++s) {
-        if (sweeps_per_sample > 0) enqueue_sweeps(c, sweeps_per_sample, (unsigned long long)s * sweeps_per_sample);
+        if (sweeps_per_sample > 0) enqueue_updates(c, sweeps_per_sample, (unsigned long long)s * sweeps_per_sample);
         launch_rgnn(c->planes[c->cur], c->L, c->n_replicas, c->rgnn_W, h, nullptr, nullptr, c->rgnn_acc, 1, c->stream);
     }
     if (n_samples > 0 && sweeps_per_sample > 0) {

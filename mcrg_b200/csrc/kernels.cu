@@ -567,6 +567,115 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_resident(const ResidentArg
     }
 }
 
+// ---- Swendsen-Wang cluster update -------------------------------------------------------------------------------
+// One lane per site, one warp per packed word (32 same-colour sites of one row).  k_sw_init: every site its own root.
+// k_sw_union: draw the +x and +y bonds of every site (one Philox call per site) and merge with a lock-free union-find
+// whose hooks always point from the larger to the smaller root (atomicMin), so the final root of a cluster is its
+// smallest site index whatever the interleaving.  k_sw_flip: find the root, flip the site iff the root's coin is set;
+// the 32 decisions of a word are gathered with a ballot and applied with one XOR.
+__device__ __forceinline__ int sw_find(const int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        x = p;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+// find with path halving.  parent[x] <= x always (hooks and shortcuts only ever point to a smaller index of the same
+// cluster-to-be), so a racing plain store of an ancestor can neither create a cycle nor disconnect anything for good:
+// whoever replaced parent[x] by a hook keeps uniting the previous parent with the hook target (sw_unite below).
+__device__ __forceinline__ int sw_find_halving(int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        const int g = __ldcg(parent + p);
+        if (g != p) __stcg(parent + x, g);
+        x = p;
+        p = g;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void sw_unite(int *parent, int a, int b) {
+    while (true) {
+        a = sw_find_halving(parent, a);
+        b = sw_find_halving(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const int tmp = a;
+            a = b;
+            b = tmp;
+        }
+        const int old = atomicMin(parent + a, b);  // hook root a under the smaller root b
+        if (old == a) return;                      // a was still a root: done
+        a = old;                                   // somebody hooked a first: continue from where it points now
+    }
+}
+
+struct SwSite {
+    size_t r;
+    int c, y, w, lane, x, i;
+    bool active;
+};
+
+__device__ __forceinline__ SwSite sw_site(const SwArgs &a, size_t n_warps) {
+    SwSite s;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    s.lane = threadIdx.x & 31;
+    s.active = warp < n_warps && s.lane < a.bits;
+    const size_t wq = warp < n_warps ? warp : 0;
+    s.w = (int)(wq % a.W);
+    const size_t ry = wq / a.W;
+    s.y = (int)(ry % a.L);
+    const size_t rc = ry / a.L;
+    s.c = (int)(rc & 1);
+    s.r = rc >> 1;
+    s.x = 2 * (32 * s.w + s.lane) + ((s.y + s.c) & 1);
+    if (s.x >= a.L) s.x = 0, s.active = false;
+    s.i = s.y * a.L + s.x;
+    return s;
+}
+
+__global__ void k_sw_init(int *parent, size_t n, size_t n_sites) {
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+        parent[idx] = (int)(idx % n_sites);  // indices are local to the replica
+}
+
+__global__ void __launch_bounds__(256) k_sw_union(const SwArgs a, size_t n_warps, int n_sites) {
+    const SwSite s = sw_site(a, n_warps);
+    if (!s.active) return;
+    const int L = a.L, W = a.W, o = 1 - s.c;
+    const uint32_t *pl = a.planes + s.r * 2 * (size_t)L * W;
+    const uint32_t mask = valid_mask(a.bits);
+    const uint32_t tw = pl[((size_t)s.c * L + s.y) * W + s.w];
+    const uint32_t dw = pl[((size_t)o * L + ((s.y + 1) & (L - 1))) * W + s.w];
+    const uint32_t *orow = pl + ((size_t)o * L + s.y) * W;
+    uint32_t rw = orow[s.w];
+    if ((s.y + s.c) & 1) rw = shift_up_index(rw, orow[(s.w + 1) & (W - 1)], a.bits, mask);  // x+1 lives at index x'+1
+    const uint32_t anti = a.anti[s.r];
+    const bool sat_r = !(((tw ^ rw ^ anti) >> s.lane) & 1u), sat_d = !(((tw ^ dw ^ anti) >> s.lane) & 1u);
+    if (!sat_r && !sat_d) return;
+    const unsigned long long t = *a.d_t + a.t_off;
+    const U4 u = philox_keyed(a.seed, (uint32_t)s.i, a.replica_base + (uint32_t)s.r, t, PURPOSE_SW_BOND, 0);
+    const uint32_t TP = a.TP[s.r];
+    int *parent = a.parent + s.r * (size_t)n_sites;
+    if (sat_r && u.x < TP) sw_unite(parent, s.i, s.y * L + ((s.x + 1) & (L - 1)));
+    if (sat_d && u.y < TP) sw_unite(parent, s.i, ((s.y + 1) & (L - 1)) * L + s.x);
+}
+
+__global__ void __launch_bounds__(256) k_sw_flip(const SwArgs a, size_t n_warps, int n_sites) {
+    const SwSite s = sw_site(a, n_warps);
+    bool flip = false;
+    if (s.active) {
+        const int root = sw_find(a.parent + s.r * (size_t)n_sites, s.i);
+        const unsigned long long t = *a.d_t + a.t_off;
+        flip = (philox_keyed(a.seed, (uint32_t)root, a.replica_base + (uint32_t)s.r, t, PURPOSE_SW_FLIP, 0).x & 1u) != 0u;
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, flip);
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (s.lane == 0 && warp < n_warps && m) a.planes[(s.r * 2 + s.c) * (size_t)a.L * a.W + (size_t)s.y * a.W + s.w] ^= m;
+}
+
 // ---- RGNN (rgnn.cpp:281-339): scalar output of the b=2 filter pyramid and its central-difference gradient ---------
 // One thread per (replica, variant): variant 0 = W, variants 1..8 = W +- h on one weight (rgnn.cpp:321-331).  The
 // pyramid is walked depth-first in Morton order with a log2(L)-deep stack, in the oracle's operation order and with
@@ -785,6 +894,15 @@ int sweep0_max_smem() {
     return g_max_smem;
 }
 
+
+void launch_sw_update(const SwArgs &a, int n_replicas, cudaStream_t st) {
+    const size_t n_sites = (size_t)a.L * a.L, n = (size_t)n_replicas * n_sites;
+    const size_t n_warps = (size_t)n_replicas * 2 * a.L * a.W;
+    const unsigned blocks = (unsigned)((n_warps + 7) / 8);
+    k_sw_init<<<(unsigned)((n + 255) / 256 > 148 * 32 ? 148 * 32 : (n + 255) / 256), 256, 0, st>>>(a.parent, n, n_sites);
+    k_sw_union<<<blocks, 256, 0, st>>>(a, n_warps, (int)n_sites);
+    k_sw_flip<<<blocks, 256, 0, st>>>(a, n_warps, (int)n_sites);
+}
 
 void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st) {
     sweep0_max_smem();

@@ -111,6 +111,20 @@ MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
     return o;
 }
 
+// Swendsen-Wang cluster update (stands in for the reference's Wolff update, ising.cpp:87-155)
+struct SwArgs {
+    uint32_t *planes;          // [replica][colour][y][w], flipped in place
+    int *parent;               // [replica][L*L] union-find forest, root = smallest site index of the cluster
+    const uint32_t *TP;        // per replica: floor((1 - exp(-2|K|)) 2^32), the bond probability of ising.cpp:9
+    const uint32_t *anti;
+    const unsigned long long *d_t;
+    unsigned long long t_off;
+    uint64_t seed;
+    uint32_t replica_base;
+    int L, W, bits;
+};
+void launch_sw_update(const SwArgs &a, int n_replicas, cudaStream_t st);
+
 void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st);
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st);
 void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st);

@@ -70,6 +70,8 @@ struct Settings {
     int device;             // MCRG_DEVICE
     std::uint64_t seed;     // MCRG_SEED
     int quiet;              // MCRG_QUIET: suppress banners
+    int cluster;            // MCRG_UPDATE=cluster: Swendsen-Wang updates (the reference's family, ising.cpp:87-155)
+                            // instead of Metropolis sweeps; sweeps_per_update then counts cluster updates
 };
 Settings &settings();
 }  // namespace mcrg_b200

@@ -82,7 +82,13 @@ static long env_long(const char *name, long dflt) {
 Settings &settings() {
     static Settings s = {(int)env_long("MCRG_REPLICAS", 1024), (int)env_long("MCRG_SWEEPS_PER_UPDATE", 1),
                          (int)env_long("MCRG_DEVICE", 0), (std::uint64_t)env_long("MCRG_SEED", 12345),
-                         (int)env_long("MCRG_QUIET", 0)};
+                         (int)env_long("MCRG_QUIET", 0), 0};
+    static bool parsed = false;
+    if (!parsed) {
+        const char *u = std::getenv("MCRG_UPDATE");
+        s.cluster = (u && (std::string(u) == "cluster" || std::string(u) == "sw")) ? 1 : 0;
+        parsed = true;
+    }
     if (s.replicas < 1) s.replicas = 1;
     if (s.sweeps_per_update < 1) s.sweeps_per_update = 1;
     return s;
@@ -93,6 +99,7 @@ struct DeviceBatch {
     int L = 0, replicas = 0;
     DeviceBatch(int L_, int replicas_, std::uint32_t replica_base) : L(L_), replicas(replicas_) {
         ck(mcrg_ctx_create(settings().device, L, replicas, settings().seed, replica_base, 1, &ctx), "mcrg_ctx_create");
+        if (settings().cluster) ck(mcrg_set_update(ctx, MCRG_UPDATE_CLUSTER), "mcrg_set_update");
     }
     ~DeviceBatch() { mcrg_ctx_destroy(ctx); }
     DeviceBatch(const DeviceBatch &) = delete;

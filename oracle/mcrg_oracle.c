@@ -413,6 +413,51 @@ void orc_metropolis(int L, int32_t *spins, double K, uint64_t seed, uint32_t rep
     }
 }
 
+static int uf_find(int *parent, int x) {
+    while (parent[x] != x) {
+        parent[x] = parent[parent[x]];
+        x = parent[x];
+    }
+    return x;
+}
+
+void orc_swendsen_wang(int L, int32_t *spins, double K, uint64_t seed, uint32_t replica, uint64_t t0, int n_updates) {
+    const int n = L * L;
+    int *parent = (int *)malloc(sizeof(int) * (size_t)n);
+    double pd = floor((1.0 - exp(-2.0 * fabs(K))) * 4294967296.0);
+    if (pd > 4294967295.0) pd = 4294967295.0;
+    const uint32_t TP = (uint32_t)pd;
+    const int ferro = (K <= 0.0);
+    for (int u = 0; u < n_updates; ++u) {
+        const uint64_t t = t0 + (uint64_t)u;
+        for (int i = 0; i < n; ++i) parent[i] = i;
+        for (int y = 0; y < L; ++y)
+            for (int x = 0; x < L; ++x) {
+                const int i = y * L + x;
+                const int nb[2] = {y * L + (x + 1) % L, ((y + 1) % L) * L + x};
+                uint32_t r[4];
+                orc_philox_keyed(seed, (uint32_t)i, replica, t, ORC_PURPOSE_SW_BOND, 0, r);
+                for (int d = 0; d < 2; ++d) {
+                    const int satisfied = ferro ? (spins[i] == spins[nb[d]]) : (spins[i] != spins[nb[d]]);
+                    if (satisfied && r[d] < TP) {
+                        int a = uf_find(parent, i), b = uf_find(parent, nb[d]);
+                        if (a != b) {
+                            if (a < b) parent[b] = a;  /* the root is always the smallest index of the cluster */
+                            else parent[a] = b;
+                        }
+                    }
+                }
+            }
+        for (int i = 0; i < n; ++i) {
+            const int root = uf_find(parent, i);
+            uint32_t r[4];
+            orc_philox_keyed(seed, (uint32_t)root, replica, t, ORC_PURPOSE_SW_FLIP, 0, r);
+            if (r[0] & 1u) spins[i] = -spins[i];
+        }
+    }
+    free(parent);
+}
+
 double orc_metropolis_timing(int L, double K, int n_sweeps, uint64_t seed) {
     /* A plain one-spin-per-byte checkerboard Metropolis with a table of acceptance thresholds and xorshift64*;
      * used only to quote a scalar CPU attempts/s figure next to the GPU number.  Returns seconds. */

@@ -26,7 +26,7 @@ extern "C" {
 
 /* ---- (S) Philox4x32-10 and the keying conventions shared with the CUDA kernels ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-enum { ORC_PURPOSE_MC = 1, ORC_PURPOSE_TIE = 2, ORC_PURPOSE_INIT = 3 };
+enum { ORC_PURPOSE_MC = 1, ORC_PURPOSE_TIE = 2, ORC_PURPOSE_INIT = 3, ORC_PURPOSE_SW_BOND = 4, ORC_PURPOSE_SW_FLIP = 5 };
 /* counter = (word, replica, t_lo, purpose<<28 | j<<20 | t_hi(20 bits)); key = (seed_lo, seed_hi) */
 void orc_philox_keyed(uint64_t seed, uint32_t word, uint32_t replica, uint64_t t, int purpose, int j,
                       uint32_t out[4]);
@@ -81,6 +81,12 @@ int orc_n_transformations(int N, int b);
 void orc_hot_start(int L, uint64_t seed, uint32_t replica, int32_t *spins);
 /* n_sweeps full checkerboard sweeps (black = (i+j) even first, then white), starting at sweep counter t0 */
 void orc_metropolis(int L, int32_t *spins, double K, uint64_t seed, uint32_t replica, uint64_t t0, int n_sweeps);
+/* (S) n Swendsen-Wang cluster updates.  Bond between site (x,y) and its +x / +y neighbour: active iff the bond is
+ * satisfied (equal spins for K<0) and U < floor((1-exp(-2|K|)) 2^32), the add probability of ising.cpp:9, with
+ * U = element 0 (+x) / 1 (+y) of Philox(word = y*L+x, purpose SW_BOND); every cluster flips iff bit 0 of
+ * Philox(word = smallest y*L+x in the cluster, purpose SW_FLIP).x is set.  Same stationary distribution as the
+ * reference's Wolff update (ising.cpp:87-155). */
+void orc_swendsen_wang(int L, int32_t *spins, double K, uint64_t seed, uint32_t replica, uint64_t t0, int n_updates);
 /* plain scalar Metropolis with a xorshift generator, for CPU timing only (attempts/s baseline) */
 double orc_metropolis_timing(int L, double K, int n_sweeps, uint64_t seed);
 

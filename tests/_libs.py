@@ -68,6 +68,7 @@ def oracle():
         o.orc_n_transformations.restype = C.c_int
         o.orc_hot_start.argtypes = [C.c_int, C.c_uint64, C.c_uint32, i32p]
         o.orc_metropolis.argtypes = [C.c_int, i32p, C.c_double, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
+        o.orc_swendsen_wang.argtypes = [C.c_int, i32p, C.c_double, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
         o.orc_metropolis_timing.argtypes = [C.c_int, C.c_double, C.c_int, C.c_uint64]
         o.orc_metropolis_timing.restype = C.c_double
         o.orc_rgnn_scalar_output.argtypes = [C.c_int, i32p, C.c_int, f64p]

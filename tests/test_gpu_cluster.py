@@ -1,0 +1,180 @@
+"""Swendsen-Wang cluster update on the device (stands in for the reference's Wolff update,
+ising.cpp:87-155): bit-exact against the scalar specification orc_swendsen_wang on the same Philox keys — the
+union-find runs in parallel with atomics, its result (root = smallest site index of each cluster) does not depend on
+the interleaving — and statistically (3 sigma) against the reference's own Wolff sampler and MCRG driver."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _libs
+from test_gpu_parity import cpu_run, oracle_hot
+from test_gpu_statistics import grouped
+
+pytestmark = pytest.mark.gpu
+
+KC = -0.5 * np.log(1 + np.sqrt(2))
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "statistical.json")
+
+
+@pytest.fixture(scope="module")
+def mc():
+    import mcrg_b200
+
+    assert mcrg_b200.capi.device_count() >= 1
+    return mcrg_b200
+
+
+@pytest.mark.parametrize("L,n_updates", [(2, 6), (4, 6), (8, 5), (16, 5), (32, 4), (64, 4), (128, 3), (256, 3), (1024, 2)])
+def test_cluster_updates_match_scalar_specification(mc, L, n_updates):
+    o = _libs.oracle()
+    seed, base, t0 = 99, 3, 500
+    Ks = [KC, -0.30, +0.44, -0.60]
+    with mc.Context(L, len(Ks), seed=seed, replica_base=base) as ctx:
+        ctx.set_update("cluster")
+        ctx.set_couplings(Ks)
+        ctx.init_hot()
+        ctx.sweep_counter = t0
+        ctx.sweep(n_updates)
+        got = ctx.get_spins()
+        assert ctx.sweep_counter == t0 + n_updates
+    for r, K in enumerate(Ks):
+        want = oracle_hot(L, seed, base + r)
+        o.orc_swendsen_wang(L, want, K, seed, base + r, t0, n_updates)
+        assert np.array_equal(got[r], want), (L, r, K, int((got[r] != want).sum()))
+
+
+def test_cluster_update_on_ordered_and_patterned_lattices(mc):
+    """One giant cluster (cold start, strong coupling), the antiferromagnetic ground state at K > 0, stripes."""
+    o = _libs.oracle()
+    L, seed = 64, 5
+    pats = _libs.pattern_lattices(L)
+    names = sorted(pats)
+    for K in (-2.0, +2.0, KC):
+        with mc.Context(L, len(names), seed=seed) as ctx:
+            ctx.set_update("cluster")
+            ctx.set_couplings([K])
+            ctx.set_spins(np.stack([pats[n] for n in names]))
+            ctx.sweep(3)
+            got = ctx.get_spins()
+        for r, n in enumerate(names):
+            want = pats[n].copy()
+            o.orc_swendsen_wang(L, want, K, seed, r, 0, 3)
+            assert np.array_equal(got[r], want), (K, n)
+
+
+@pytest.mark.parametrize("L,n_samples,m,graphs", [(8, 6, 1, 0), (64, 20, 2, 1), (256, 5, 1, 0)])
+def test_run_with_cluster_updates_matches_oracle(mc, L, n_samples, m, graphs):
+    seed, base, t0 = 31, 0, 40
+    Ks = [KC, -0.43]
+    lay = mc.capi.acc_layout()
+    with mc.Context(L, 2, seed=seed, replica_base=base) as ctx:
+        ctx.set_update("cluster")
+        ctx.set_tuning(use_graphs=graphs)
+        ctx.set_couplings(Ks)
+        ctx.init_hot()
+        ctx.sweep_counter = t0
+        ctx.run(n_samples, m, -1, 0)
+        acc, accd = ctx.accumulators()
+        final = ctx.get_spins()
+    for r in range(2):
+        want = cpu_run(L, seed, base + r, Ks[r], t0, n_samples, m, -1, oracle_hot(L, seed, base + r), update="cluster")
+        a = acc[r, 0]
+        assert a[lay.slot_n] == want["n"] and a[lay.slot_absm] == want["absM"] and a[lay.slot_m2] == want["M2"]
+        for k in range(3 * (want["n_lv"] + 1)):
+            assert a[lay.slot_s + k] == int(want["S"][k])
+        for n in range(want["n_lv"]):
+            for e in range(9):
+                assert a[lay.slot_sbs + n * 9 + e] == want["SbS"][n * 9 + e]
+        assert np.array_equal(final[r], want["final"])
+
+
+def test_switching_update_modes_keeps_one_chain(mc):
+    """Metropolis sweeps and cluster updates can be interleaved on one context; each consumes one counter tick."""
+    o = _libs.oracle()
+    L, seed = 32, 8
+    with mc.Context(L, 1, seed=seed) as ctx:
+        ctx.init_hot()
+        ctx.sweep(2)
+        ctx.set_update("cluster")
+        ctx.sweep(2)
+        ctx.set_update("metropolis")
+        ctx.sweep(1)
+        got = ctx.get_spins()[0]
+    want = oracle_hot(L, seed, 0)
+    o.orc_metropolis(L, want, KC, seed, 0, 0, 2)
+    o.orc_swendsen_wang(L, want, KC, seed, 0, 2, 2)
+    o.orc_metropolis(L, want, KC, seed, 0, 4, 1)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("L,K", [(8, KC), (16, KC), (32, KC), (64, KC), (16, -0.40), (16, -0.48)])
+def test_cluster_thermodynamics_match_reference_wolff(mc, L, K):
+    with open(GOLD) as f:
+        ref = next(t for t in json.load(f)["thermo"] if t["N"] == L and abs(t["K"] - K) < 1e-9)
+    lay = mc.capi.acc_layout()
+    with mc.Context(L, 512, seed=4000 + L) as ctx:
+        ctx.set_update("cluster")
+        ctx.set_couplings([K])
+        ctx.init_hot()
+        ctx.sweep(200)
+        ctx.run(1500, 1, 0, 0)
+        acc, accd = ctx.accumulators()
+    N = L * L
+
+    def obs(v):
+        n = float(v[lay.slot_n])
+        m2 = float(v[lay.slot_m2]) / n / N**2
+        m4 = float(v[-1]) / n / float(N) ** 4
+        return np.array([float(v[lay.slot_s]) / n / (4.0 * N), float(v[lay.slot_absm]) / n / N, m2, m4, 1.0 - m4 / (3.0 * m2 * m2)])
+
+    est, err = mc.analysis.jackknife(grouped(acc[:, 0, :], accd[:, 0, :], 32), obs)
+    for k, name in enumerate(["bond", "absm", "m2", "m4", "U4"]):
+        want, want_err = ref[name]
+        sigma = np.hypot(err[k], want_err)
+        assert abs(est[k] - want) < 3.0 * sigma, (L, K, name, est[k], err[k], want, want_err)
+
+
+def test_cluster_rg_eigenvalues_match_reference_driver(mc):
+    """lambda per level at L = 64, K_c with the cluster update (no critical slowing down: one update per sample,
+    exactly the reference's schedule mcrg.cpp:72-98) against the reference driver's values."""
+    with open(GOLD) as f:
+        ref = next(t for t in json.load(f)["lambda"] if t["N"] == 64)
+    n_lv = 5
+    with mc.Context(64, 512, seed=123) as ctx:
+        ctx.set_update("cluster")
+        ctx.init_hot()
+        ctx.sweep(300)
+        ctx.run(3000, 1, -1, 0)
+        acc, accd = ctx.accumulators()
+
+    def lambdas(v):
+        return mc.analysis.rg_eigenvalues(mc.analysis.unpack_slots(v[:-1], n_lv), ops=(0, 1))[0]
+
+    est, err = mc.analysis.jackknife(grouped(acc[:, 0, :], accd[:, 0, :], 32), lambdas)
+    for lv in range(n_lv):
+        sigma = np.hypot(err[lv], ref["err"][lv])
+        assert abs(est[lv] - ref["mean"][lv]) < 3.0 * sigma, (lv, est[lv], err[lv], ref["mean"][lv], ref["err"][lv])
+    assert abs(est[1] - 2.0) < 0.03
+
+
+def test_cluster_update_at_full_size(mc):
+    """L = 4096: properties that need no oracle — determinism, |M| of a cold strongly coupled lattice is conserved
+    (one cluster), and the update decorrelates a critical lattice far faster than a Metropolis sweep."""
+    L = 4096
+    with mc.Context(L, 2, seed=77) as ctx:
+        ctx.set_update("cluster")
+        ctx.set_couplings([-3.0, KC])
+        ctx.init_cold()
+        ctx.sweep(2)
+        M = ctx.observables()["M"]
+        assert abs(int(M[0])) > 0.999 * L * L
+        a = ctx.get_spins(1, 1)[0]
+    with mc.Context(L, 2, seed=77) as ctx:
+        ctx.set_update("cluster")
+        ctx.set_couplings([-3.0, KC])
+        ctx.init_cold()
+        ctx.sweep(2)
+        b = ctx.get_spins(1, 1)[0]
+    assert np.array_equal(a, b)

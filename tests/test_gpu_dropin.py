@@ -64,6 +64,21 @@ def test_calc_critical_exponent_matches_reference_driver(tmp_path):
         assert abs(float(rows[lv].split(",")[1]) - lam) < 1e-9
 
 
+def test_calc_critical_exponent_with_cluster_updates(tmp_path):
+    """MCRG_UPDATE=cluster: the driver keeps the reference's schedule — ONE (cluster) update per sample, mcrg.cpp:72-98
+    — and reproduces the reference driver's lambda per level."""
+    with open(os.path.join(_libs.ROOT, "tests", "golden", "statistical.json")) as f:
+        ref = next(t for t in json.load(f)["lambda"] if t["N"] == 32)
+    out = run([APP, "exponent", "32", repr(KC), "300", "2000000"], tmp_path,
+              {"MCRG_REPLICAS": "1024", "MCRG_UPDATE": "cluster", "MCRG_SEED": "99", "MCRG_QUIET": "1"})
+    res = re.findall(r"RESULT level (\d+) lambda (\S+) err (\S+) nu (\S+)", out)
+    assert len(res) == 4
+    for lv, lam, err, nu in res:
+        lv, lam, err = int(lv), float(lam), float(err)
+        sigma = np.hypot(err, ref["err"][lv])
+        assert abs(lam - ref["mean"][lv]) < 3 * sigma, (lv, lam, err, ref["mean"][lv], ref["err"][lv])
+
+
 def test_locate_critical_point(tmp_path):
     """Two-lattice matching (mcrg.cpp:146-310).  The reference's own result for L = 16 is K_c(16) = -0.440414806
     (main.cpp:26); it is a fixed point of the iteration, so start there and expect to stay within errors."""

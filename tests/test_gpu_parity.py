@@ -281,7 +281,7 @@ def test_full_size_pyramid_properties(mc):
 # the sample loop and its accumulators   (exact 128-bit integers)
 # ---------------------------------------------------------------------------------------------------------
 
-def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start):
+def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start, update="metropolis"):
     """mcrg_run's contract restated with the oracle: per sample measure (pyramid with Philox ties keyed by the
     sweep counter), accumulate (mcrg.cpp:86-97, exact), then m sweeps."""
     o = _libs.oracle()
@@ -309,7 +309,7 @@ def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start):
                         SB0[lv - 1][b * 3 + a] += int(S3[lv, a]) * int(S3[0, b])
         M = int(S4[0, 3])
         absM += abs(M); M2 += M * M; M4 += float(M) ** 4
-        o.orc_metropolis(L, s, K, seed, replica, t, m)
+        (o.orc_swendsen_wang if update == "cluster" else o.orc_metropolis)(L, s, K, seed, replica, t, m)
         t += m
     SbS = [int(h) * (1 << 64) + int(l) for h, l in zip(hi1, lo1)]
     SbSb = [int(h) * (1 << 64) + int(l) for h, l in zip(hi2, lo2)]
