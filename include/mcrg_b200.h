@@ -82,6 +82,13 @@ int mcrg_init_cold(mcrg_ctx *ctx);
 /* Lattice(int a, imat spins) (lattice.cpp:18-30) / reading Lattice::spins_ (lattice.hpp:16) */
 int mcrg_set_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, const int32_t *host_spins);
 int mcrg_get_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, int32_t *host_spins);
+/* Pipelined form of mcrg_set_spins_i32_colmajor for drivers that stream configurations through the device:
+ * _begin starts copying `count` replicas from PINNED host memory to a device buffer on a separate copy stream and
+ * returns at once — the copy overlaps whatever the context's stream is running; _commit makes the context's stream
+ * wait for that copy and packs it into the lattices (replacing replicas [first, first+count)).  One upload in flight
+ * per context; the host buffer may be reused after _commit and mcrg_sync. */
+int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *ctx, int first, int count, const int32_t *pinned_host_spins);
+int mcrg_set_spins_commit(mcrg_ctx *ctx);
 /* block spins produced by the last measurement; level in 1..levels of that measurement; (L>>level)^2 ints */
 int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *ctx, int replica, int level, int32_t *host_spins);
 int mcrg_get_sweep_counter(mcrg_ctx *ctx, uint64_t *t);

@@ -54,6 +54,8 @@ def lib():
         l.mcrg_init_cold.argtypes = [vp]
         l.mcrg_set_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_get_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
+        l.mcrg_set_spins_i32_colmajor_begin.argtypes = [vp, C.c_int, C.c_int, vp]
+        l.mcrg_set_spins_commit.argtypes = [vp]
         l.mcrg_get_level_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_get_sweep_counter.argtypes = [vp, P(C.c_uint64)]
         l.mcrg_set_sweep_counter.argtypes = [vp, C.c_uint64]
@@ -168,6 +170,13 @@ class Context:
     def set_spins_ptr(self, host_ptr, count, first=0):
         """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
         _check(lib().mcrg_set_spins_i32_colmajor(self._h, first, count, C.c_void_p(host_ptr)))
+
+    def set_spins_begin(self, host_ptr, count, first=0):
+        """Start an asynchronous upload from PINNED host memory (copy stream); pair with set_spins_commit()."""
+        _check(lib().mcrg_set_spins_i32_colmajor_begin(self._h, first, count, C.c_void_p(host_ptr)))
+
+    def set_spins_commit(self):
+        _check(lib().mcrg_set_spins_commit(self._h))
 
     def get_spins(self, first=0, count=None):
         count = self.n_replicas - first if count is None else count

@@ -80,6 +80,13 @@ struct mcrg_ctx {
     double *rgnn_W = nullptr, *rgnn_acc = nullptr, *rgnn_u = nullptr, *rgnn_grad = nullptr;
     int32_t *stage = nullptr;
     size_t stage_ints = 0;
+    // pipelined upload (mcrg_set_spins_i32_colmajor_begin / _commit): copy stream + its own device buffer
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_packed = nullptr;
+    int32_t *upload = nullptr;
+    size_t upload_ints = 0;
+    int up_first = 0, up_count = 0;
+    bool up_pending = false, up_packed_recorded = false;
     int last_levels = 0;
     bool measured = false;
     int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
@@ -449,6 +456,11 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->rgnn_u);
     cudaFree(c->rgnn_grad);
     cudaFree(c->stage);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->upload);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int p = 0; p < 2; ++p) {
@@ -571,6 +583,50 @@ int mcrg_set_spins_i32_colmajor(mcrg_ctx *c, int first, int count, const int32_t
         CK(cudaGetLastError());
         if (done + k < (size_t)count) CK(cudaStreamSynchronize(c->stream));  // staging buffer is reused
     }
+    return 0;
+}
+
+int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *c, int first, int count, const int32_t *pinned_host) {
+    if (!c || !pinned_host) return fail(MCRG_ERR_ARG, "null pointer");
+    if (first < 0 || count < 1 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
+    if (c->up_pending) return fail(MCRG_ERR_STATE, "an upload is already in flight: call mcrg_set_spins_commit first");
+    CK(cudaSetDevice(c->device));
+    const size_t ints = (size_t)count * c->L * c->L;
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    }
+    if (c->upload_ints < ints) {
+        CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->upload) cudaFree(c->upload);
+        c->upload = nullptr;
+        c->upload_ints = 0;
+        CK(cudaMalloc(&c->upload, ints * sizeof(int32_t)));
+        c->upload_ints = ints;
+        c->up_packed_recorded = false;
+    }
+    // the previous commit's pack kernel must have consumed the buffer before it is overwritten
+    if (c->up_packed_recorded) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed, 0));
+    CK(cudaMemcpyAsync(c->upload, pinned_host, ints * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->up_first = first;
+    c->up_count = count;
+    c->up_pending = true;
+    return 0;
+}
+
+int mcrg_set_spins_commit(mcrg_ctx *c) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (!c->up_pending) return fail(MCRG_ERR_STATE, "no upload in flight");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    launch_pack0(c->upload, c->planes[c->cur] + (size_t)c->up_first * 2 * c->L * c->W, c->L, c->up_count, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_packed, c->stream));
+    c->up_packed_recorded = true;
+    c->up_pending = false;
     return 0;
 }
 

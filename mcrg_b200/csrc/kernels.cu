@@ -13,8 +13,10 @@
 //                      accumulation of mcrg.cpp:86-97 (S, S(n) x S(n-1), S(n) x S(n)) into exact 128-bit sums.
 #include "kernels.cuh"
 
+// 3 CTAs of 256 threads per SM = 80 registers per thread: the row body of mc_row keeps its constants in registers
+// (measured: 0.274 ms per launch of the headline configuration against 0.286 ms with 4 CTAs / 64 registers)
 #ifndef MCRG_SWEEP_MIN_BLOCKS
-#define MCRG_SWEEP_MIN_BLOCKS 4
+#define MCRG_SWEEP_MIN_BLOCKS 3
 #endif
 
 namespace mcrg {
@@ -108,7 +110,7 @@ __device__ __forceinline__ U4 mc_philox(uint64_t seed, uint32_t word_id, uint32_
 }
 
 struct McQueue {
-    uint32_t *ent;   // [warp][cap][3]: tile word offset, undecided lanes, selector (A==1 lanes)
+    uint4 *ent;      // [warp][cap]: {tile word offset, undecided lanes, selector (A==1 lanes), -}
     int cap;         // entries per warp
 };
 
@@ -120,78 +122,164 @@ __device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0,
     return lt;
 }
 
-// One half-sweep (colour c) over local rows [lr_lo, lr_lo + nrows).  A thread keeps its column w and walks down the
-// rows with a constant stride, so word offsets are incremental.  Words that still have undecided lanes after the 8
-// planes of pass 1 are appended to a queue PRIVATE TO THE WARP (slot = warp-uniform running count + rank in the
-// ballot: no atomics, no shuffles) and finished densely by the same warp — only __syncwarp() between the passes.
+// One half-sweep (colour c) over local rows [lr_lo, lr_lo + nrows).
+// Thread layout: column w = tid & (W-1), row group g = tid >> lw; a group owns a CONTIGUOUS block of rows and every
+// thread walks down its column.  The other-colour words above / at / below the current row then form a sliding window
+// in registers (one new load per row instead of three), all shared-memory addresses are "pointer + constant", and the
+// direction of the in-row neighbour shift — which alternates with the row parity — is a template parameter of the
+// row body (rows are processed in pairs).  For 32-bit words the shift is one funnel shift.
+// Words that still have undecided lanes after the 8 planes of pass 1 are appended to a queue PRIVATE TO THE WARP
+// (slot = warp-uniform running count + rank in the ballot: no atomics, no shuffles) and finished densely by the same
+// warp — only __syncwarp() between the passes.  Every warp executes the same number of row steps (inactive steps are
+// predicated off), so the ballots are full-warp even when a warp spans several row groups (W < 32).
+struct McWalk {
+    uint32_t *pc;        // this thread's word of the row being updated
+    const uint32_t *po;  // the same position in the other colour's plane
+    uint32_t u, n0;      // other-colour words of rows lr-1 and lr
+    uint32_t yw;         // (y_first + lr) << lw, NOT wrapped: the word id masks it
+    uint32_t off;        // word offset of pc inside its plane (queue entries carry it)
+    int n_queued;        // warp-uniform
+};
+
+struct McConst {
+    uint4 *my_q;         // this warp's queue segment: {offset, undecided lanes, selector, -}
+    const McTable *tab;
+    uint64_t seed;
+    uint32_t replica, t_lo, c3_base, anti, mask, wid_c, yw_mask, lanes_below;
+    int W, bits, d_up, d_dn, qcap, n_act;
+};
+
+// word id of the Philox counter: colour*L*W + y*W + w.  wid_c = colour*L*W + w and (yw & yw_mask) = (y mod L)*W occupy
+// disjoint bits, so one LOP3 builds it from the running row counter.
+__device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g) { return (k.yw & g.yw_mask) | g.wid_c; }
+
+template <int P, bool B32>
+__device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
+    uint32_t eq = 0, sel = 0;
+    if (it < g.n_act) {
+        const uint32_t t = *k.pc;
+        const uint32_t d = k.po[g.W];
+        uint32_t n1;
+        if (P) {
+            const uint32_t nb = k.po[g.d_up];
+            n1 = B32 ? __funnelshift_r(k.n0, nb, 1) : shift_up_index(k.n0, nb, g.bits, g.mask);
+        } else {
+            const uint32_t nb = k.po[g.d_dn];
+            n1 = B32 ? __funnelshift_l(nb, k.n0, 1) : shift_down_index(k.n0, nb, g.bits, g.mask);
+        }
+        const uint32_t a1 = t ^ k.u ^ g.anti, a2 = t ^ d ^ g.anti, a3 = t ^ k.n0 ^ g.anti, a4 = t ^ n1 ^ g.anti;
+        const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
+        // lanes with A >= 2 flip unconditionally; fold them in now so that only one word stays live
+        uint32_t t2 = t ^ (B32 ? (c12 | c34 | (x12 & x34)) : ((c12 | c34 | (x12 & x34)) & g.mask));
+        sel = (x12 ^ x34) & ~(c12 | c34);   // A == 1
+        eq = sel | ~(a1 | a2 | a3 | a4);    // A == 1 or A == 0: lanes that need a random number
+        if (!B32) {
+            sel &= g.mask;
+            eq &= g.mask;
+        }
+        uint32_t lt = 0;                    // subset of the initial eq, hence disjoint from the A >= 2 lanes
+        const uint32_t word_id = mc_word_id(k, g);
+        const U4 r0 = mc_philox(g.seed, word_id, g.replica, g.t_lo, g.c3_base, 0);
+        const U4 r1 = mc_philox(g.seed, word_id, g.replica, g.t_lo, g.c3_base, 1);
+        mc_compare4(r0, g.tab, 0, sel, eq, lt);
+        mc_compare4(r1, g.tab, 4, sel, eq, lt);
+        *k.pc = t2 ^ lt;
+        k.u = k.n0;
+        k.n0 = d;
+    }
+    // ~10 % of the words keep undecided lanes, i.e. almost every warp-row has a few: keep this block short
+    const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);
+    if (eq != 0u) {
+        const int slot = k.n_queued + __popc(pend & g.lanes_below);
+        if (slot < g.qcap) {
+            g.my_q[slot] = make_uint4(k.off, eq, sel, 0u);
+        } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
+            *k.pc ^= mc_finish(eq, sel, 2, g.tab, g.seed, mc_word_id(k, g), g.replica, g.t_lo, g.c3_base);
+        }
+    }
+    k.n_queued += __popc(pend);
+    k.pc += g.W;
+    k.po += g.W;
+    k.off += (uint32_t)g.W;
+    k.yw += (uint32_t)g.W;
+}
+
+template <int P0, bool B32>
+__device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
+    for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
+        mc_row<P0, B32>(k, g, it);
+        mc_row<1 - P0, B32>(k, g, it + 1);
+    }
+}
+
+template <int WT>
+__device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
+                                                const McTable *tab, const McQueue &q, uint64_t seed, uint32_t replica,
+                                                unsigned long long sweep) {
+    const int W = WT > 0 ? WT : s.W, o = 1 - c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *plane_c = s.base + c * s.rows * W;
+    const uint32_t *plane_o = s.base + o * s.rows * W;
+    McConst g;
+    g.my_q = q.ent + q.cap * warp;  // this warp's segment: q.cap entries
+    g.tab = tab;
+    g.seed = seed;
+    g.replica = replica;
+    g.t_lo = (uint32_t)sweep;
+    g.c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
+    g.anti = anti;
+    g.mask = s.mask;
+    g.lanes_below = (1u << lane) - 1u;
+    g.W = W;
+    g.bits = s.bits;
+    g.qcap = q.cap;
+    const int w = threadIdx.x & (W - 1), grp = threadIdx.x >> lw;
+    const int n_grp = blockDim.x >> lw;  // blockDim is a multiple of W (launch_sweep0)
+    g.d_up = ((w + 1) & (W - 1)) - w;
+    g.d_dn = ((w - 1) & (W - 1)) - w;
+    g.wid_c = (uint32_t)(c * s.L * W + w);
+    g.yw_mask = (uint32_t)((s.L - 1) << lw);
+    // rows per group: even when a warp spans several groups (their row parities must agree), else just the ceiling
+    int chunk = (nrows + n_grp - 1) / n_grp;
+    if (W < 32) chunk = (chunk + 1) & ~1;
+    const int n_steps = (chunk + 1) & ~1;  // identical for every thread
+    const int lr_hi = lr_lo + nrows;
+    int lr0 = lr_lo + grp * chunk, lr1 = lr0 + chunk;
+    if (lr1 > lr_hi) lr1 = lr_hi;
+    if (lr0 >= lr_hi) lr0 = lr1 = lr_lo;  // nothing to do: park on a valid row
+    g.n_act = lr1 - lr0;
+    McWalk k;
+    k.off = (uint32_t)(lr0 * W + w);
+    k.pc = plane_c + k.off;
+    k.po = plane_o + k.off;
+    k.u = k.po[-W];
+    k.n0 = k.po[0];
+    k.yw = (uint32_t)((s.y_first + lr0) << lw);
+    k.n_queued = 0;
+    const int par0 = (s.y_first + lr0 + c) & 1;  // warp-uniform (W >= 32: one group per warp; W < 32: chunk even)
+    if (s.bits == 32) {
+        if (par0) mc_walk<1, true>(k, g, n_steps);
+        else mc_walk<0, true>(k, g, n_steps);
+    } else {
+        if (par0) mc_walk<1, false>(k, g, n_steps);
+        else mc_walk<0, false>(k, g, n_steps);
+    }
+    __syncwarp();
+    const int total = min(k.n_queued, q.cap);
+    for (int e = lane; e < total; e += 32) {
+        const uint4 ent = g.my_q[e];
+        const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
+        const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
+        plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, seed, word_id, replica, g.t_lo, g.c3_base);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
                                               const McTable *tab, const McQueue &q, uint64_t seed, uint32_t replica,
                                               unsigned long long sweep) {
-    const int W = s.W, o = 1 - c;
-    const uint32_t t_lo = (uint32_t)sweep;
-    const uint32_t c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
-    uint32_t *plane_c = s.base + c * s.rows * W;
-    const uint32_t *plane_o = s.base + o * s.rows * W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lanes_below = (1u << lane) - 1u;
-    uint32_t *my_q = q.ent + 3 * q.cap * warp;  // this warp's segment: q.cap entries
-    const int w = threadIdx.x & (W - 1);
-    const int row_step = blockDim.x >> lw;  // blockDim is a multiple of W (launch_sweep0)
-    const int d_up = ((w + 1) & (W - 1)) - w, d_dn = ((w - 1) & (W - 1)) - w;
-    const int lr_hi = lr_lo + nrows;
-    const int n_iter = (nrows + row_step - 1) / row_step;  // identical for every thread: ballots are full-warp
-    const uint32_t wid_base = (uint32_t)(c * s.L * W + w);
-    int lr = lr_lo + (threadIdx.x >> lw);
-    int n_queued = 0;  // warp-uniform
-    for (int it = 0; it < n_iter; ++it, lr += row_step) {
-        uint32_t eq = 0, sel = 0, off = 0;
-        if (lr < lr_hi) {
-            off = (uint32_t)(lr * W + w);
-            const int y = (s.y_first + lr) & (s.L - 1);
-            const uint32_t t = plane_c[off];
-            const uint32_t u = plane_o[off - W], d = plane_o[off + W], n0 = plane_o[off];
-            uint32_t n1;
-            if ((y + c) & 1) n1 = shift_up_index(n0, plane_o[off + d_up], s.bits, s.mask);
-            else n1 = shift_down_index(n0, plane_o[off + d_dn], s.bits, s.mask);
-            const uint32_t a1 = t ^ u ^ anti, a2 = t ^ d ^ anti, a3 = t ^ n0 ^ anti, a4 = t ^ n1 ^ anti;
-            const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
-            // lanes with A >= 2 flip unconditionally; fold them in now so that only one word stays live
-            const uint32_t t2 = t ^ ((c12 | c34 | (x12 & x34)) & s.mask);
-            sel = (x12 ^ x34) & ~(c12 | c34) & s.mask;   // A == 1
-            eq = (sel | ~(a1 | a2 | a3 | a4)) & s.mask;  // A == 1 or A == 0: lanes that need a random number
-            uint32_t lt = 0;                             // subset of the initial eq, hence disjoint from the A >= 2 lanes
-            if (eq) {
-                const uint32_t word_id = wid_base + ((uint32_t)y << lw);
-                const U4 r0 = mc_philox(seed, word_id, replica, t_lo, c3_base, 0);
-                const U4 r1 = mc_philox(seed, word_id, replica, t_lo, c3_base, 1);
-                mc_compare4(r0, tab, 0, sel, eq, lt);
-                mc_compare4(r1, tab, 4, sel, eq, lt);
-            }
-            plane_c[off] = t2 ^ lt;
-        }
-        const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);  // ~10 % of the words
-        if (eq != 0u) {
-            const int slot = n_queued + __popc(pend & lanes_below);
-            if (slot < q.cap) {
-                my_q[3 * slot + 0] = off;
-                my_q[3 * slot + 1] = eq;
-                my_q[3 * slot + 2] = sel;
-            } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
-                const int y = (s.y_first + ((int)off >> lw)) & (s.L - 1);
-                plane_c[off] ^= mc_finish(eq, sel, 2, tab, seed, wid_base + ((uint32_t)y << lw), replica, t_lo, c3_base);
-            }
-        }
-        n_queued += __popc(pend);
-    }
-    __syncwarp();
-    const int total = min(n_queued, q.cap);
-    for (int e = lane; e < total; e += 32) {
-        const uint32_t off = my_q[3 * e + 0];
-        const int y = (s.y_first + ((int)off >> lw)) & (s.L - 1);
-        const uint32_t word_id = (uint32_t)(c * s.L * W) + ((uint32_t)y << lw) + (off & (uint32_t)(W - 1));
-        plane_c[off] ^= mc_finish(my_q[3 * e + 1], my_q[3 * e + 2], 2, tab, seed, word_id, replica, t_lo, c3_base);
-    }
-    __syncthreads();
+    if (s.W == 64) mc_half_sweep_t<64>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);  // L = 4096
+    else mc_half_sweep_t<0>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
 }
 
 template <bool MEASURE>
@@ -248,7 +336,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
 
     if (a.nsw > 0) {
         McQueue q;
-        q.ent = smem + 2 * rows * W;
+        q.ent = reinterpret_cast<uint4 *>(smem + ((2 * rows * W + 3) & ~3));
         q.cap = sweep0_queue_cap(rows * W, blockDim.x >> 5);
         const uint32_t anti = a.anti[r];
         for (int h = 0; h < 2 * a.nsw; ++h)
@@ -470,7 +558,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_resident(const ResidentArg
     s.y_first = L - 1;
     const ResidentLayout lay = resident_layout(L, blockDim.x, a.n_levels);
     McQueue q;
-    q.ent = smem + lay.queue_off;
+    q.ent = reinterpret_cast<uint4 *>(smem + lay.queue_off);
     q.cap = lay.cap;
     uint32_t *bufA = smem + lay.bufA_off, *bufB = smem + lay.bufB_off;
     unsigned long long *acc_lo = reinterpret_cast<unsigned long long *>(smem + lay.acc_off);
@@ -873,7 +961,7 @@ int sweep0_threads(int L, int R, int H) {
 size_t sweep0_smem_bytes(int L, int R, int H) {
     const int words = (R + 2 * H) * l0_words(L);
     const int warps = sweep0_threads(L, R, H) / 32;
-    return ((size_t)2 * words + (size_t)3 * warps * sweep0_queue_cap(words, warps)) * sizeof(uint32_t);
+    return ((((size_t)2 * words + 3) & ~(size_t)3) + (size_t)4 * warps * sweep0_queue_cap(words, warps)) * sizeof(uint32_t);
 }
 
 int sweep0_max_smem() {

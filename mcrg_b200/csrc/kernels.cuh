@@ -13,8 +13,8 @@ constexpr int TAIL_MAX_L = 256;         // blocked lattices up to this size fini
 constexpr int SWEEP_THREADS = 256;
 // capacity of a warp's "still undecided after 8 bit planes" queue for a strip with `words` words per colour
 // (expected fill: ~10 % of the words)
-// per warp: a quarter of the words a warp handles in one half-sweep, at least 16 entries
-MCRG_HD int sweep0_queue_cap(int words, int warps) { const int c = (words / warps + 3) / 4; return c > 16 ? c : 16; }
+// per warp: a fifth of the words a warp handles in one half-sweep, at least 16 entries (16 bytes each)
+MCRG_HD int sweep0_queue_cap(int words, int warps) { const int c = (words / warps + 4) / 5; return c > 16 ? c : 16; }
 
 // accumulator slots (per replica, per bin), all exact 128-bit integers (lo: uint64, hi: int64)
 constexpr int SLOT_N = 0;                                    // samples
@@ -102,7 +102,7 @@ MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
     const int W = l0_words(L), words = (L + 2) * W, warps = threads / 32;
     o.cap = sweep0_queue_cap(words, warps);
     o.queue_off = (2 * words + 3) & ~3;
-    o.bufA_off = (o.queue_off + 3 * o.cap * warps + 3) & ~3;
+    o.bufA_off = o.queue_off + 4 * o.cap * warps;
     const int L1 = L / 2 > 0 ? L / 2 : 1, L2 = L / 4 > 0 ? L / 4 : 1;
     o.bufB_off = (o.bufA_off + L1 * nat_words(L1) + 3) & ~3;
     o.acc_off = (o.bufB_off + L2 * nat_words(L2) + 3) & ~3;

@@ -99,6 +99,40 @@ def test_rg_eigenvalues_match_reference_driver(mc, gold, L, m, n_samples):
     assert abs(est[1] - 2.0) < 0.03
 
 
+EXACT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exact_ising.json")
+
+
+@pytest.mark.parametrize("update,m", [("metropolis", 4), ("cluster", 1)])
+@pytest.mark.parametrize("L,absK", [(4, 0.4406867935097715), (4, 0.40), (8, 0.4406867935097715), (8, 0.489652),
+                                    (16, 0.4406867935097715), (16, 0.48), (32, 0.4406867935097715), (64, 0.4406867935097715)])
+def test_energy_matches_exact_finite_size_solution(mc, update, m, L, absK):
+    """<s s'> on nearest-neighbour bonds against Kaufman's exact torus partition function (tests/golden/make_exact.py):
+    a known answer with no statistical error of its own, for both samplers, ferro- and antiferromagnetic sign."""
+    with open(EXACT) as f:
+        ex = json.load(f)
+    want = next(t for t in ex["kaufman_bond"] if t["L"] == L and abs(t["absK"] - absK) < 1e-12)["bond"]
+    lay = mc.capi.acc_layout()
+    for sign in (-1.0, +1.0):
+        n_rep = 4096 if L <= 16 else 1024
+        with mc.Context(L, n_rep, seed=600 + L + (7 if sign > 0 else 0)) as ctx:
+            ctx.set_update(update)
+            ctx.set_couplings([sign * absK])
+            ctx.init_hot()
+            ctx.sweep(100 * m * (L // 4) if update == "metropolis" else 100)
+            ctx.run(1000, m * max(1, L // 8) if update == "metropolis" else 1, 0, 0)
+            acc, accd = ctx.accumulators()
+        per = np.array([float(acc[r, 0, lay.slot_s]) / float(acc[r, 0, lay.slot_n]) / (4.0 * L * L) for r in range(n_rep)])
+        mean, err = per.mean(), per.std(ddof=1) / np.sqrt(n_rep)
+        assert abs(mean - (-sign) * want) < N_SIGMA * err, (update, L, sign * absK, mean, err, want, (mean + sign * want) / err)
+        if L == 4 and sign < 0 and any(abs(t["absK"] - absK) < 1e-12 for t in ex["enum_4x4"]):
+            e4 = next(t for t in ex["enum_4x4"] if abs(t["absK"] - absK) < 1e-12)
+            absm = np.array([float(acc[r, 0, lay.slot_absm]) / float(acc[r, 0, lay.slot_n]) / 16.0 for r in range(n_rep)])
+            m2 = np.array([float(acc[r, 0, lay.slot_m2]) / float(acc[r, 0, lay.slot_n]) / 256.0 for r in range(n_rep)])
+            m4 = accd[:, 0, 0] / np.array([float(acc[r, 0, lay.slot_n]) for r in range(n_rep)]) / 16.0**4
+            for name, v in (("absm", absm), ("m2", m2), ("m4", m4)):
+                assert abs(v.mean() - e4[name]) < N_SIGMA * v.std(ddof=1) / np.sqrt(n_rep), (update, name, v.mean(), e4[name])
+
+
 def test_three_operator_matrix_and_antiferromagnet(mc):
     """Extensions without a reference counterpart, pinned by physics: (i) adding the plaquette operator keeps
     lambda_t near 2; (ii) K > 0 at |K| = K_c is the same model on the bipartite lattice (staggered gauge), so the
