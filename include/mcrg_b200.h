@@ -90,6 +90,13 @@ int mcrg_get_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, int32_t *ho
 int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *ctx, int first, int count, const int32_t *pinned_host_spins);
 int mcrg_set_spins_commit(mcrg_ctx *ctx);
 /* block spins produced by the last measurement; level in 1..levels of that measurement; (L>>level)^2 ints */
+/* The same upload with the 32-fold smaller PCIe transfer: pack on the host (plain CPU code on `n_threads` threads, no
+ * device work; 1 bit per spin, replica-major, internal row y = reference column j, max(1, L/32) words per row, bit k
+ * of word w = spin (i = 32w+k, j = y) is +1), then hand the packed words to the device.  mcrg_set_spins_packed is
+ * stream-ordered (asynchronous for pinned `packed`); the buffer must stay valid until the next synchronising call. */
+size_t mcrg_packed_words(int L, int count);
+int mcrg_host_pack_i32_colmajor(const int32_t *host_spins, int L, int count, uint32_t *packed, int n_threads);
+int mcrg_set_spins_packed(mcrg_ctx *ctx, int first, int count, const uint32_t *packed);
 int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *ctx, int replica, int level, int32_t *host_spins);
 int mcrg_get_sweep_counter(mcrg_ctx *ctx, uint64_t *t);
 int mcrg_set_sweep_counter(mcrg_ctx *ctx, uint64_t t);

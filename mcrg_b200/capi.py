@@ -56,6 +56,10 @@ def lib():
         l.mcrg_get_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_set_spins_i32_colmajor_begin.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_set_spins_commit.argtypes = [vp]
+        l.mcrg_packed_words.argtypes = [C.c_int, C.c_int]
+        l.mcrg_packed_words.restype = C.c_size_t
+        l.mcrg_host_pack_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
+        l.mcrg_set_spins_packed.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_get_level_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_get_sweep_counter.argtypes = [vp, P(C.c_uint64)]
         l.mcrg_set_sweep_counter.argtypes = [vp, C.c_uint64]
@@ -96,6 +100,15 @@ def acc_layout():
 
 def levels_full(L):
     return lib().mcrg_levels_full(L)
+
+
+def packed_words(L, count):
+    return lib().mcrg_packed_words(L, count)
+
+
+def host_pack(spins_ptr, L, count, packed_ptr, n_threads=1):
+    """int32 column-major host configurations -> 1 bit/spin transport words, on the host (mcrg_host_pack_i32_colmajor)."""
+    _check(lib().mcrg_host_pack_i32_colmajor(C.c_void_p(spins_ptr), L, count, C.c_void_p(packed_ptr), n_threads))
 
 
 class Context:
@@ -177,6 +190,10 @@ class Context:
 
     def set_spins_commit(self):
         _check(lib().mcrg_set_spins_commit(self._h))
+
+    def set_spins_packed_ptr(self, packed_ptr, count, first=0):
+        """Upload host-packed configurations (host_pack); stream-ordered, asynchronous for pinned memory."""
+        _check(lib().mcrg_set_spins_packed(self._h, first, count, C.c_void_p(packed_ptr)))
 
     def get_spins(self, first=0, count=None):
         count = self.n_replicas - first if count is None else count

@@ -586,6 +586,20 @@ int mcrg_set_spins_i32_colmajor(mcrg_ctx *c, int first, int count, const int32_t
     return 0;
 }
 
+int mcrg_set_spins_packed(mcrg_ctx *c, int first, int count, const uint32_t *packed) {
+    if (!c || !packed) return fail(MCRG_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t words = mcrg_packed_words(c->L, count);
+    int rc = ensure_stage(c, words);  // 1 bit per spin: the staging buffer is small
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->stage, packed, words * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_pack_nat(reinterpret_cast<const uint32_t *>(c->stage), c->planes[c->cur] + (size_t)first * 2 * c->L * c->W, c->L, count, c->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *c, int first, int count, const int32_t *pinned_host) {
     if (!c || !pinned_host) return fail(MCRG_ERR_ARG, "null pointer");
     if (first < 0 || count < 1 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);

@@ -39,7 +39,11 @@ __device__ __forceinline__ void warp_reduce_to(const Counts &c, unsigned int *ce
     }
 }
 
-// rows [row_lo, row_lo+nrows) of a [*, W] word array: global -> shared, periodic in y (L a power of two)
+// rows [row_lo, row_lo+nrows) of a [*, W] word array: global -> shared, periodic in y (L a power of two).
+// 16-byte asynchronous copies (cp.async.cg: L2 -> shared memory without a register round trip), so that every copy of
+// a thread is in flight at once; stage_wait() before the barrier that publishes the tile.
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W,
                                            int L) {
     if ((W & 3) == 0) {  // W is a power of two: shifts, not divisions
@@ -47,7 +51,8 @@ __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_pl
         for (int idx = threadIdx.x; idx < n4; idx += blockDim.x) {
             const int lr = idx >> l4, w4 = idx & (W4 - 1);
             const int y = (y_first + lr) & (L - 1);
-            reinterpret_cast<uint4 *>(dst)[idx] = __ldg(reinterpret_cast<const uint4 *>(src_plane + (size_t)y * W) + w4);
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint4 *>(dst) + idx);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(reinterpret_cast<const uint4 *>(src_plane + (size_t)y * W) + w4) : "memory");
         }
     } else {
         const int lw = ilog2(W), n = nrows << lw;
@@ -311,6 +316,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     }
     const unsigned long long t = *a.d_t + a.t_off;
     const uint32_t replica = a.replica_base + (uint32_t)r;
+    stage_wait();
     __syncthreads();
 
     if (MEASURE) {
@@ -363,6 +369,7 @@ __global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
     const unsigned long long t = *a.d_t + a.t_off;
     const uint32_t replica = a.replica_base + (uint32_t)r;
+    stage_wait();
     __syncthreads();
 
     Counts c = {0u, 0u, 0u, 0u};
@@ -494,6 +501,7 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
         const int Ln = a.L >> a.start, Wn = nat_words(Ln);
         stage_rows(bufA, a.in + (size_t)r * Ln * Wn, 0, Ln, Wn, Ln);
     }
+    stage_wait();
     __syncthreads();
     pyramid_in_smem(bufA, bufB, a.L, a.start, a.n_levels, red, a.levels_out, a.level_off, r, a.seed, replica, t);
     // raw popcounts -> the reference's sums; levels below `start` were counted by k_sweep0 / k_level
@@ -538,7 +546,7 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
 // (2W words) instead of recomputed.  Global memory is touched at the start (load), at the end (store, accumulator
 // flush) and nowhere in between; the accumulators of the launch live in shared memory as exact 128-bit sums.
 template <bool MEASURE>
-__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_resident(const ResidentArgs a) {
+__global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_resident(const ResidentArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
     __shared__ long long S_sh[(MAX_LEVELS + 1) * 4];
@@ -579,6 +587,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_resident(const ResidentArg
         }
     const uint32_t anti = a.anti[r];
     double m4 = 0.0;
+    stage_wait();
     __syncthreads();
 
     for (int smp = 0; smp < a.n_samples; ++smp) {
@@ -893,6 +902,32 @@ __global__ void k_pack0(const int32_t *spins, uint32_t *planes, int L, int W, si
     }
 }
 
+// packed natural transport format (hostpack.cpp: row y, bit x, max(1, L/32) words per row) -> colour planes.
+// One thread per (replica, row, colour-plane word w): the word's 32 sites x = 2x'+par come from natural words 2w, 2w+1.
+__global__ void k_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int W, int bits, size_t n) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int w = (int)(idx % W);
+    const size_t ry = idx / W;
+    const int y = (int)(ry % L);
+    const size_t r = ry / L;
+    const int Wn = nat_words(L);
+    const uint32_t *row = nat + (r * L + y) * (size_t)Wn;
+    uint32_t even, odd;
+    if (Wn == 1) {
+        even = compress_even(row[0]);
+        odd = compress_even(row[0] >> 1);
+    } else {
+        const uint32_t a = row[2 * w], b = row[2 * w + 1];
+        even = compress_even(a) | (compress_even(b) << 16);
+        odd = compress_even(a >> 1) | (compress_even(b >> 1) << 16);
+    }
+    const uint32_t mask = valid_mask(bits);
+    const int ce = y & 1;  // plane whose row offset is 0 holds the even-x sites
+    planes[((r * 2 + ce) * L + y) * W + w] = even & mask;
+    planes[((r * 2 + (1 - ce)) * L + y) * W + w] = odd & mask;
+}
+
 __global__ void k_unpack0(const uint32_t *planes, int32_t *spins, int L, int W, size_t n_warps) {
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -1049,6 +1084,12 @@ void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas,
     const int W = l0_words(L);
     const size_t n_warps = (size_t)n_replicas * L * W;
     k_pack0<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(spins, planes, L, W, n_warps);
+}
+
+void launch_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
+    const int W = l0_words(L);
+    const size_t n = (size_t)n_replicas * L * W;
+    k_pack_nat<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nat, planes, L, W, l0_bits(L), n);
 }
 
 void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st) {

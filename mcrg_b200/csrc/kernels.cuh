@@ -136,6 +136,7 @@ void launch_advance_t(unsigned long long *d_t, unsigned long long by, cudaStream
 void launch_init_hot(uint32_t *planes, int L, int n_replicas, uint64_t seed, uint32_t replica_base, cudaStream_t st);
 void launch_init_cold(uint32_t *planes, int L, int n_replicas, cudaStream_t st);
 void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas, cudaStream_t st);
+void launch_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int n_replicas, cudaStream_t st);
 void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st);
 void launch_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int n_replicas, cudaStream_t st);
 size_t sweep0_smem_bytes(int L, int R, int H);

@@ -131,6 +131,24 @@ def test_limb_encoding_roundtrip(mc):
     assert mc.dist.limbs_to_ints(limbs + limbs[::-1]) == [a + b for a, b in zip(vals, vals[::-1])]
 
 
+@pytest.mark.parametrize("L", [2, 4, 16, 32, 64, 256])
+def test_host_pack_matches_numpy(mc, L):
+    """mcrg_host_pack_i32_colmajor (host-side format conversion, no device): bit k of word w of row y = spin (32w+k, y)."""
+    rng = np.random.default_rng(L)
+    n = 3
+    spins = np.where(rng.random((n, L, L)) < 0.5, 1, -1).astype(np.int32)
+    out = np.zeros(mc.capi.packed_words(L, n), np.uint32)
+    for threads in (1, 3):
+        out[:] = 0
+        mc.capi.host_pack(spins.ctypes.data, L, n, out.ctypes.data, threads)
+        bits = min(32, L)
+        flat = (spins > 0).reshape(-1, bits)
+        want = np.zeros(flat.shape[0], np.uint32)
+        for k in range(bits):
+            want |= flat[:, k].astype(np.uint32) << np.uint32(k)
+        assert np.array_equal(out, want)
+
+
 def test_shard_replicas(mc):
     for n, w in ((40, 1), (40, 8), (5, 2), (7, 4), (4096, 8), (3, 8)):
         seen = []
