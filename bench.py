@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
 
         # third form: pack on the host (1 bit/spin, all host threads) while the previous block runs on the GPU, upload
         # the packed words (32x fewer PCIe bytes).  Same host inputs (int32 imat in pinned memory), same results.
-        n_thr = os.cpu_count() or 1
+        n_thr = max(1, (os.cpu_count() or 1) // world)  # ranks share the host cores
         pk = [torch.empty(capi.packed_words(L, n_loc), dtype=torch.int32).pin_memory() for _ in range(2)]
 
         def e2e_packed(n):
