@@ -75,6 +75,7 @@ struct mcrg_ctx {
     uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr, *TP = nullptr;
     int update_mode = MCRG_UPDATE_METROPOLIS;
     int *sw_parent = nullptr;  // union-find forest of the cluster update, allocated by mcrg_set_update
+    uint32_t *sw_coins = nullptr;  // cluster coin bitmap, 1 bit per site (rounded up to 128 per replica)
     unsigned long long *d_t = nullptr;
     unsigned long long t_host = 0;
     double *rgnn_W = nullptr, *rgnn_acc = nullptr, *rgnn_u = nullptr, *rgnn_grad = nullptr;
@@ -176,6 +177,7 @@ void enqueue_cluster_updates(mcrg_ctx *c, int n, unsigned long long t_off) {
     SwArgs a;
     a.planes = c->planes[c->cur];
     a.parent = c->sw_parent;
+    a.coins = c->sw_coins;
     a.TP = c->TP;
     a.anti = c->anti;
     a.d_t = c->d_t;
@@ -450,6 +452,7 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->anti);
     cudaFree(c->TP);
     cudaFree(c->sw_parent);
+    cudaFree(c->sw_coins);
     cudaFree(c->d_t);
     cudaFree(c->rgnn_W);
     cudaFree(c->rgnn_acc);
@@ -514,8 +517,10 @@ int mcrg_set_update(mcrg_ctx *c, int mode) {
     if (!c) return fail(MCRG_ERR_ARG, "null context");
     if (mode != MCRG_UPDATE_METROPOLIS && mode != MCRG_UPDATE_CLUSTER) return fail(MCRG_ERR_ARG, "unknown update mode %d", mode);
     CK(cudaSetDevice(c->device));
-    if (mode == MCRG_UPDATE_CLUSTER && !c->sw_parent)
+    if (mode == MCRG_UPDATE_CLUSTER && !c->sw_parent) {
         CK(cudaMalloc(&c->sw_parent, (size_t)c->n_replicas * c->L * c->L * sizeof(int)));
+        CK(cudaMalloc(&c->sw_coins, (size_t)c->n_replicas * (((size_t)c->L * c->L + 127) / 128) * 16));
+    }
     c->update_mode = mode;
     return 0;
 }

@@ -115,6 +115,7 @@ MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
 struct SwArgs {
     uint32_t *planes;          // [replica][colour][y][w], flipped in place
     int *parent;               // [replica][L*L] union-find forest, root = smallest site index of the cluster
+    uint32_t *coins;           // [replica][ceil(L*L/128)][4] cluster coins, bit i = coin of the cluster rooted at site i
     const uint32_t *TP;        // per replica: floor((1 - exp(-2|K|)) 2^32), the bond probability of ising.cpp:9
     const uint32_t *anti;
     const unsigned long long *d_t;

@@ -451,8 +451,8 @@ void orc_swendsen_wang(int L, int32_t *spins, double K, uint64_t seed, uint32_t 
         for (int i = 0; i < n; ++i) {
             const int root = uf_find(parent, i);
             uint32_t r[4];
-            orc_philox_keyed(seed, (uint32_t)root, replica, t, ORC_PURPOSE_SW_FLIP, 0, r);
-            if (r[0] & 1u) spins[i] = -spins[i];
+            orc_philox_keyed(seed, (uint32_t)root >> 7, replica, t, ORC_PURPOSE_SW_FLIP, 0, r);
+            if ((r[((uint32_t)root >> 5) & 3u] >> ((uint32_t)root & 31u)) & 1u) spins[i] = -spins[i];
         }
     }
     free(parent);

@@ -83,8 +83,9 @@ void orc_hot_start(int L, uint64_t seed, uint32_t replica, int32_t *spins);
 void orc_metropolis(int L, int32_t *spins, double K, uint64_t seed, uint32_t replica, uint64_t t0, int n_sweeps);
 /* (S) n Swendsen-Wang cluster updates.  Bond between site (x,y) and its +x / +y neighbour: active iff the bond is
  * satisfied (equal spins for K<0) and U < floor((1-exp(-2|K|)) 2^32), the add probability of ising.cpp:9, with
- * U = element 0 (+x) / 1 (+y) of Philox(word = y*L+x, purpose SW_BOND); every cluster flips iff bit 0 of
- * Philox(word = smallest y*L+x in the cluster, purpose SW_FLIP).x is set.  Same stationary distribution as the
+ * U = element 0 (+x) / 1 (+y) of Philox(word = y*L+x, purpose SW_BOND); every cluster flips iff its coin is set, the
+ * coin of a cluster being bit (root & 127) of the 128-bit output of Philox(word = root >> 7, purpose SW_FLIP) with
+ * root = smallest y*L+x in the cluster (element (root >> 5) & 3, bit root & 31): one call serves 128 site indices.  Same stationary distribution as the
  * reference's Wolff update (ising.cpp:87-155). */
 void orc_swendsen_wang(int L, int32_t *spins, double K, uint64_t seed, uint32_t replica, uint64_t t0, int n_updates);
 /* plain scalar Metropolis with a xorshift generator, for CPU timing only (attempts/s baseline) */
