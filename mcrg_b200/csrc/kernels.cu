@@ -44,6 +44,82 @@ __device__ __forceinline__ void warp_reduce_to(const Counts &c, unsigned int *ce
 // a thread is in flight at once; stage_wait() before the barrier that publishes the tile.
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, one instruction per contiguous run of rows) + mbarrier -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(
+            smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// rows [y_first, y_first + nrows) (periodic) of one plane -> shared memory, issued by ONE thread: one bulk copy per
+// contiguous run of rows (two when the strip wraps around the lattice edge).  Returns the bytes put in flight.
+__device__ __forceinline__ uint32_t bulk_stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W, int L,
+                                                    unsigned long long *bar) {
+    int y = y_first, left = nrows;
+    uint32_t total = 0;
+    while (left > 0) {
+        const int n = left < L - y ? left : L - y;
+        const uint32_t bytes = (uint32_t)n * (uint32_t)W * 4u;
+        bulk_g2s(dst, src_plane + (size_t)y * W, bytes, bar);
+        dst += n * W;
+        total += bytes;
+        left -= n;
+        y = 0;
+    }
+    return total;
+}
+
+// Staging entry points used by every kernel: TMA when the rows are 16-byte multiples, else cp.async / plain loads.
+// Protocol: tile_stage_begin (all threads; contains a barrier when TMA is used), tile_stage_plane per plane with the SAME
+// total byte count announced up front, tile_stage_wait (all threads), then the caller's __syncthreads().
+__device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W, int L);
+
+__device__ __forceinline__ bool tile_stage_begin(unsigned long long *bar, int W, uint32_t total_bytes) {
+    const bool tma = (W & 3) == 0;
+    if (tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_proxy_async();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_expect_tx(bar, total_bytes);
+    }
+    return tma;
+}
+__device__ __forceinline__ void tile_stage_plane(bool tma, unsigned long long *bar, uint32_t *dst, const uint32_t *src_plane,
+                                                 int y_first, int nrows, int W, int L) {
+    if (tma) {
+        if (threadIdx.x == 0) bulk_stage_rows(dst, src_plane, y_first, nrows, W, L, bar);
+    } else {
+        stage_rows(dst, src_plane, y_first, nrows, W, L);
+    }
+}
+__device__ __forceinline__ void tile_stage_wait(bool tma, unsigned long long *bar) {
+    if (tma) mbar_wait(bar, 0);
+    else stage_wait();
+}
+
 __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W,
                                            int L) {
     if ((W & 3) == 0) {  // W is a power of two: shifts, not divisions
@@ -292,6 +368,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[4];
     __shared__ __align__(16) McTable tab;
+    __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.y, strip = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
     const int rows = a.R + 2 * a.H;
@@ -305,8 +382,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     s.L = L;
     s.y_first = (y0 - a.H) & (L - 1);
     const uint32_t *src_r = a.src + (size_t)r * 2 * L * W;
-    stage_rows(s0_plane(s, 0), src_r, s.y_first, rows, W, L);
-    stage_rows(s0_plane(s, 1), src_r + (size_t)L * W, s.y_first, rows, W, L);
+    // staging: TMA bulk copies signalled through an mbarrier when rows are 16-byte multiples (L >= 256), else cp.async / loads
+    const bool tma = tile_stage_begin(&bar, W, 2u * (uint32_t)rows * (uint32_t)W * 4u);
+    tile_stage_plane(tma, &bar, s0_plane(s, 0), src_r, s.y_first, rows, W, L);
+    tile_stage_plane(tma, &bar, s0_plane(s, 1), src_r + (size_t)L * W, s.y_first, rows, W, L);
     if (MEASURE && threadIdx.x < 4) red[threadIdx.x] = 0;
     if (a.nsw > 0) {
         for (int k = threadIdx.x; k < 64; k += blockDim.x) {  // blockDim may be as small as 32
@@ -316,7 +395,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     }
     const unsigned long long t = *a.d_t + a.t_off;
     const uint32_t replica = a.replica_base + (uint32_t)r;
-    stage_wait();
+    tile_stage_wait(tma, &bar);
     __syncthreads();
 
     if (MEASURE) {
@@ -349,14 +428,26 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
             mc_half_sweep(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, a.seed, replica,
                           t + (unsigned long long)(h >> 1));
         uint32_t *dst_r = a.dst + (size_t)r * 2 * L * W;
-        unstage_rows(dst_r, s0_plane(s, 0) + a.H * W, y0, a.R, W, L);
-        unstage_rows(dst_r + (size_t)L * W, s0_plane(s, 1) + a.H * W, y0, a.R, W, L);
+        if (tma) {  // the R rows of a strip are contiguous in global memory: one bulk store per colour plane
+            fence_proxy_async();  // this thread's shared-memory writes become visible to the copy engine ...
+            __syncthreads();      // ... and so do everybody else's
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = (uint32_t)a.R * (uint32_t)W * 4u;
+                bulk_s2g(dst_r + (size_t)y0 * W, s0_plane(s, 0) + a.H * W, bytes);
+                bulk_s2g(dst_r + (size_t)L * W + (size_t)y0 * W, s0_plane(s, 1) + a.H * W, bytes);
+                bulk_commit_wait_read();  // shared memory must stay alive until the engine has read it
+            }
+        } else {
+            unstage_rows(dst_r, s0_plane(s, 0) + a.H * W, y0, a.R, W, L);
+            unstage_rows(dst_r + (size_t)L * W, s0_plane(s, 1) + a.H * W, y0, a.R, W, L);
+        }
     }
 }
 
 __global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[4];
+    __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.y, strip = blockIdx.x;
     const int Ln = a.Ln, Wn = nat_words(Ln), lw = ilog2(Wn);
     const int y0 = strip * a.R;
@@ -365,11 +456,12 @@ __global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
     s.W = Wn;
     s.bits = nat_bits(Ln);
     s.mask = valid_mask(s.bits);
-    stage_rows(smem, a.in + (size_t)r * Ln * Wn, y0, a.R + 1, Wn, Ln);
+    const bool tma = tile_stage_begin(&bar, Wn, (uint32_t)(a.R + 1) * (uint32_t)Wn * 4u);
+    tile_stage_plane(tma, &bar, smem, a.in + (size_t)r * Ln * Wn, y0, a.R + 1, Wn, Ln);
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
     const unsigned long long t = *a.d_t + a.t_off;
     const uint32_t replica = a.replica_base + (uint32_t)r;
-    stage_wait();
+    tile_stage_wait(tma, &bar);
     __syncthreads();
 
     Counts c = {0u, 0u, 0u, 0u};
@@ -493,15 +585,17 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
     __shared__ __align__(16) uint32_t bufB[(TAIL_MAX_L / 2) * (TAIL_MAX_L / 64)];
     __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
     __shared__ long long S_sh[(MAX_LEVELS + 1) * 4];
+    __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.x;
     const uint32_t replica = a.replica_base + (uint32_t)r;
     const unsigned long long t = *a.d_t + a.t_off;
     for (int k = threadIdx.x; k < (MAX_LEVELS + 1) * 4; k += blockDim.x) red[k] = 0;
-    if (a.start <= a.n_levels) {
+    if (a.start <= a.n_levels) {  // uniform for the CTA
         const int Ln = a.L >> a.start, Wn = nat_words(Ln);
-        stage_rows(bufA, a.in + (size_t)r * Ln * Wn, 0, Ln, Wn, Ln);
+        const bool tma = tile_stage_begin(&bar, Wn, (uint32_t)Ln * (uint32_t)Wn * 4u);
+        tile_stage_plane(tma, &bar, bufA, a.in + (size_t)r * Ln * Wn, 0, Ln, Wn, Ln);
+        tile_stage_wait(tma, &bar);
     }
-    stage_wait();
     __syncthreads();
     pyramid_in_smem(bufA, bufB, a.L, a.start, a.n_levels, red, a.levels_out, a.level_off, r, a.seed, replica, t);
     // raw popcounts -> the reference's sums; levels below `start` were counted by k_sweep0 / k_level
@@ -551,6 +645,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
     __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
     __shared__ long long S_sh[(MAX_LEVELS + 1) * 4];
     __shared__ __align__(16) McTable tab;
+    __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
     const int rows = L + 2;
@@ -574,8 +669,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
     long long *acc_hi = reinterpret_cast<long long *>(acc_lo + n_live);
 
     uint32_t *gl = a.planes + (size_t)r * 2 * L * W;
-    stage_rows(s0_plane(s, 0), gl, s.y_first, rows, W, L);
-    stage_rows(s0_plane(s, 1), gl + (size_t)L * W, s.y_first, rows, W, L);
+    const bool tma = tile_stage_begin(&bar, W, 2u * (uint32_t)rows * (uint32_t)W * 4u);
+    tile_stage_plane(tma, &bar, s0_plane(s, 0), gl, s.y_first, rows, W, L);
+    tile_stage_plane(tma, &bar, s0_plane(s, 1), gl + (size_t)L * W, s.y_first, rows, W, L);
     for (int k = threadIdx.x; k < 64; k += blockDim.x) {
         const uint32_t T = (k & 1) ? a.T8[r] : a.T4[r];
         tab.tm[k >> 1][k & 1] = ((T >> (31 - (k >> 1))) & 1u) ? 0xFFFFFFFFu : 0u;
@@ -587,7 +683,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
         }
     const uint32_t anti = a.anti[r];
     double m4 = 0.0;
-    stage_wait();
+    tile_stage_wait(tma, &bar);
     __syncthreads();
 
     for (int smp = 0; smp < a.n_samples; ++smp) {
@@ -1232,14 +1328,14 @@ int sweep0_max_smem() {
         int dev = 0, v = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        // dynamic limit = opt-in maximum minus the kernels' few bytes of static shared memory
-        const int dyn = v - 1024;
+        // dynamic limit = opt-in maximum minus the kernels' static shared memory (k_resident: 1032 bytes)
+        const int dyn = v - 2048;
         cudaError_t e1 = cudaFuncSetAttribute(k_sweep0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaError_t e2 = cudaFuncSetAttribute(k_sweep0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaError_t e3 = cudaFuncSetAttribute(k_level, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaFuncSetAttribute(k_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaFuncSetAttribute(k_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        g_max_smem = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) ? dyn : 48 * 1024;
+        cudaError_t e4 = cudaFuncSetAttribute(k_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaError_t e5 = cudaFuncSetAttribute(k_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        g_max_smem = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess && e5 == cudaSuccess) ? dyn : 48 * 1024;
         (void)cudaGetLastError();  // a refused opt-in only lowers the limit we plan with
     }
     return g_max_smem;
