@@ -245,6 +245,20 @@ def run_ours(args, rank, world, local_rank):
         prof = ctx.profile_kernels(min(S, 32), m, -1)
         barrier()
 
+        # also the sweep-only rate and one measurement every 16 sweeps (same state, device timers, this rank)
+        def rate(fn, sweeps):
+            fn()
+            ctx.sync()
+            best = 1e30
+            for _ in range(3):
+                ctx.timer_start()
+                fn()
+                best = min(best, ctx.timer_stop())
+            return n_loc * L * L * sweeps / (best * 1e-3) / 1e9
+
+        other = {"sweep_only": rate(lambda: ctx.sweep(32), 32), "m16": rate(lambda: ctx.run(4, 16, -1, 0), 64)}
+        barrier()
+
         # ---- end to end through the C ABI with host buffers
         e2e_steps = max(5, args.steps // 2)
         host = torch.empty((n_loc, L, L), dtype=torch.int32).pin_memory()
@@ -358,6 +372,7 @@ def run_ours(args, rank, world, local_rank):
                 "variants": {"unpipelined_int32_upload": e2e_sync_value, "pipelined_int32_upload": e2e_pipe_value,
                              "host_packed_upload": e2e_packed_value}},
         "gpu_launches": launches_per_step * args.steps,
+        "other_schedules_per_gpu": {"unit": UNIT, "sweep_only": other["sweep_only"], "one_measurement_per_16_sweeps": other["m16"]},
         "roofline": {"bound": "hbm", "kernel": "k_sweep0<MEASURE> (level-0 correlators + block to level 1 + Metropolis sweep)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_SITE_DOMINANT * n_loc * L * L,

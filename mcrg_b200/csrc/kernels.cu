@@ -23,8 +23,6 @@ namespace mcrg {
 
 namespace {
 
-__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
-
 // Warp-reduce the four counters and add lane 0's totals into shared (or global) 32-bit cells.
 __device__ __forceinline__ void warp_reduce_to(const Counts &c, unsigned int *cells) {
     const unsigned int a = __reduce_add_sync(0xFFFFFFFFu, c.anti_nn);
@@ -760,545 +758,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
     }
 }
 
-// ---- Swendsen-Wang cluster update -------------------------------------------------------------------------------
-// Three kernels per update.  k_sw_tile: draw the +x and +y bonds of every site (one Philox call per site) and label the
-// clusters inside 64 x 64 tiles with a union-find in shared memory.  k_sw_border: merge across tile edges in global
-// memory.  Both use a lock-free union-find whose hooks always point from the larger to the smaller root (atomicMin), so
-// the final root of a cluster is its smallest site index whatever the interleaving — the result is bit-identical to the
-// scalar specification.  k_sw_flip (one lane per site, one warp per packed word): find the root, flip the site iff the
-// root's coin is set; the 32 decisions of a word are gathered with a ballot and applied with one XOR.
-__device__ __forceinline__ int sw_find(const int *parent, int x) {
-    int p = __ldcg(parent + x);
-    while (p != x) {
-        x = p;
-        p = __ldcg(parent + x);
-    }
-    return x;
-}
-
-// find with path halving.  parent[x] <= x always (hooks and shortcuts only ever point to a smaller index of the same
-// cluster-to-be), so a racing plain store of an ancestor can neither create a cycle nor disconnect anything for good:
-// whoever replaced parent[x] by a hook keeps uniting the previous parent with the hook target (sw_unite below).
-__device__ __forceinline__ int sw_find_halving(int *parent, int x) {
-    int p = __ldcg(parent + x);
-    while (p != x) {
-        const int g = __ldcg(parent + p);
-        if (g != p) __stcg(parent + x, g);
-        x = p;
-        p = g;
-    }
-    return x;
-}
-
-__device__ __forceinline__ void sw_unite(int *parent, int a, int b) {
-    while (true) {
-        a = sw_find_halving(parent, a);
-        b = sw_find_halving(parent, b);
-        if (a == b) return;
-        if (a < b) {
-            const int tmp = a;
-            a = b;
-            b = tmp;
-        }
-        const int old = atomicMin(parent + a, b);  // hook root a under the smaller root b
-        if (old == a) return;                      // a was still a root: done
-        a = old;                                   // somebody hooked a first: continue from where it points now
-    }
-}
-
-struct SwSite {
-    size_t r;
-    int c, y, w, lane, x, i;
-    bool active;
-};
-
-__device__ __forceinline__ SwSite sw_site(const SwArgs &a, size_t n_warps) {
-    SwSite s;
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    s.lane = threadIdx.x & 31;
-    s.active = warp < n_warps && s.lane < a.bits;
-    const size_t wq = warp < n_warps ? warp : 0;  // W and L are powers of two: shifts, not 64-bit divisions
-    const int lw = ilog2(a.W), ll = ilog2(a.L);
-    s.w = (int)(wq & (size_t)(a.W - 1));
-    const size_t ry = wq >> lw;
-    s.y = (int)(ry & (size_t)(a.L - 1));
-    const size_t rc = ry >> ll;
-    s.c = (int)(rc & 1);
-    s.r = rc >> 1;
-    s.x = 2 * (32 * s.w + s.lane) + ((s.y + s.c) & 1);
-    if (s.x >= a.L) s.x = 0, s.active = false;
-    s.i = s.y * a.L + s.x;
-    return s;
-}
-
-// spin of site (x, y) as a bit, from the colour planes of one replica in global memory
-__device__ __forceinline__ uint32_t sw_spin_bit(const uint32_t *pl, int L, int W, int x, int y) {
-    const int c = (x + y) & 1, xh = x >> 1;
-    return (pl[((size_t)c * L + y) * W + (xh >> 5)] >> (xh & 31)) & 1u;
-}
-
-// Tile phase: one CTA labels the clusters INSIDE one TW x TH tile (TW = TH = min(64, L)) with a union-find in shared
-// memory (shared atomics), then writes for every site the global index of its tile-local root: parent[] becomes a
-// forest of depth 1 whose roots are the smallest site index of every tile-local cluster.  The bonds that leave the tile
-// through its right and bottom edges (including the periodic wrap) are left to k_sw_border.  Every bond decision is the
-// same Philox draw as in orc_swendsen_wang: element 0 (+x) / 1 (+y) of the call keyed by the site index.
-constexpr int SW_TILE = 64;
-
-__device__ __forceinline__ int sw_find_smem(int *lab, int x) {
-    int p = lab[x];
-    while (p != x) {
-        const int g = lab[p];
-        if (g != p) lab[x] = g;  // path halving; labels only ever decrease, a stale store is still an ancestor
-        x = p;
-        p = g;
-    }
-    return x;
-}
-
-__device__ __forceinline__ void sw_unite_smem(int *lab, int a, int b) {
-    while (true) {
-        a = sw_find_smem(lab, a);
-        b = sw_find_smem(lab, b);
-        if (a == b) return;
-        if (a < b) {
-            const int tmp = a;
-            a = b;
-            b = tmp;
-        }
-        const int old = atomicMin(lab + a, b);
-        if (old == a) return;
-        a = old;
-    }
-}
-
-// insert a zero between the bits of a 32-bit word: bit k -> bit 2k
-__device__ __forceinline__ unsigned long long spread_bits(uint32_t v) {
-    unsigned long long x = v;
-    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
-    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
-    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
-    x = (x | (x << 2)) & 0x3333333333333333ull;
-    x = (x | (x << 1)) & 0x5555555555555555ull;
-    return x;
-}
-
-// T = 64 (L >= 64).  Rows of the tile are 64-bit masks in shared memory: spins S, active horizontal bonds HB (bit lx =
-// bond between lx and lx+1) and vertical bonds VB (bit lx = bond between rows ly and ly+1).  Horizontal runs need no
-// union-find at all: the first site of the run through (lx, ly) follows from HB[ly] with a count-leading-zeros.  The
-// union-find then only merges RUNS through vertical bonds, and only through the first bond of every stretch of bonds that
-// joins the same two runs.  Everything else as in the generic kernel below.
-__global__ void __launch_bounds__(256) k_sw_tile64(const SwArgs a, int tiles_x, int tiles_per_replica, int n_sites) {
-    constexpr int T = SW_TILE;
-    __shared__ int lab[T * T];
-    __shared__ unsigned long long S[T + 1], HB[T], VB[T];
-    __shared__ unsigned short pairs[T * T];
-    __shared__ int n_pairs;
-    const int L = a.L, W = a.W;
-    const int r = blockIdx.x / tiles_per_replica, tile = blockIdx.x - r * tiles_per_replica;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int x0 = tx * T, y0 = ty * T;
-    const uint32_t *pl = a.planes + (size_t)r * 2 * L * W;
-    const int w0 = x0 >> 6;
-    if (threadIdx.x == 0) n_pairs = 0;
-    if (threadIdx.x <= T) {  // natural-order row: the plane with (y + c) even holds the even x
-        const int y = (y0 + threadIdx.x) & (L - 1), ce = y & 1;
-        const uint32_t ev = pl[((size_t)ce * L + y) * W + w0], od = pl[((size_t)(1 - ce) * L + y) * W + w0];
-        S[threadIdx.x] = spread_bits(ev) | (spread_bits(od) << 1);
-    }
-    __syncthreads();
-    const uint32_t TP = a.TP[r];
-    const unsigned long long anti = a.anti[r] ? ~0ull : 0ull;
-    const unsigned long long t = *a.d_t + a.t_off;
-    const uint32_t replica = a.replica_base + (uint32_t)r;
-    const int lx = threadIdx.x & (T - 1), half = (threadIdx.x >> 5) & 1;
-    for (int k = 0; k < T / 4; ++k) {
-        const int ly = 4 * k + (threadIdx.x >> 6);
-        const unsigned long long row = S[ly];
-        const unsigned long long sat_r = ~(row ^ (row >> 1) ^ anti) & 0x7FFFFFFFFFFFFFFFull;  // bit lx: (lx, lx+1), lx < 63
-        const unsigned long long sat_d = ly + 1 < T ? ~(row ^ S[ly + 1] ^ anti) : 0ull;
-        const bool sr = (sat_r >> lx) & 1ull, sd = (sat_d >> lx) & 1ull;
-        bool br = false, bd = false;
-        if (sr || sd) {
-            const int i = (y0 + ly) * L + (x0 + lx);
-            const U4 u = philox_keyed(a.seed, (uint32_t)i, replica, t, PURPOSE_SW_BOND, 0);
-            br = sr && u.x < TP;
-            bd = sd && u.y < TP;
-        }
-        const uint32_t mr = __ballot_sync(0xFFFFFFFFu, br), md = __ballot_sync(0xFFFFFFFFu, bd);
-        if ((threadIdx.x & 31) == 0) {
-            reinterpret_cast<uint32_t *>(&HB[ly])[half] = mr;
-            reinterpret_cast<uint32_t *>(&VB[ly])[half] = md;
-        }
-    }
-    __syncthreads();
-    for (int k = 0; k < T / 4; ++k) {  // run labels: first site of the horizontal run
-        const int ly = 4 * k + (threadIdx.x >> 6);
-        const unsigned long long z = ~HB[ly] & ((1ull << lx) - 1ull);  // broken links below lx
-        const int rs = z ? 64 - __clzll((long long)z) : 0;
-        lab[ly * T + lx] = ly * T + rs;
-    }
-    __syncthreads();
-    // the vertical bonds that still have to be merged are sparse (about one site in five): gather them into a list
-    // (warp-aggregated append) and run the union-find densely over the list instead of with mostly idle warps
-    for (int k = 0; k < T / 4; ++k) {
-        const int ly = 4 * k + (threadIdx.x >> 6);
-        bool need = false;
-        if (ly + 1 < T) {
-            const unsigned long long vb = VB[ly];
-            // the bond one column to the left joins the same two runs if both runs continue and it is active too
-            need = ((vb >> lx) & 1ull) && !(lx > 0 && (((vb & HB[ly] & HB[ly + 1]) >> (lx - 1)) & 1ull));
-        }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
-        if (m) {
-            int base = 0;
-            if ((threadIdx.x & 31) == 0) base = atomicAdd(&n_pairs, __popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (need) pairs[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = (unsigned short)(ly * T + lx);
-        }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < n_pairs; e += blockDim.x) {
-        const int up = pairs[e];
-        sw_unite_smem(lab, lab[up], lab[up + T]);
-    }
-    __syncthreads();
-    // flatten by pointer jumping (every site in lock step, no divergent pointer chasing): lab[s] <- lab[lab[s]] until
-    // nothing changes; labels only move towards the root, so concurrent reads of half-updated entries are harmless
-    bool changed;
-    do {
-        changed = false;
-        for (int k = 0; k < T / 4; ++k) {
-            const int s = (4 * k + (threadIdx.x >> 6)) * T + lx;
-            const int p = lab[s], g = lab[p];
-            if (g != p) {
-                lab[s] = g;
-                changed = true;
-            }
-        }
-    } while (__syncthreads_or(changed));
-    int *parent = a.parent + (size_t)r * n_sites;
-    for (int k = 0; k < T / 4; ++k) {
-        const int ly = 4 * k + (threadIdx.x >> 6);
-        const int root = lab[ly * T + lx];
-        parent[(y0 + ly) * L + (x0 + lx)] = (y0 + (root >> 6)) * L + (x0 + (root & (T - 1)));
-    }
-}
-
-// Generic tile kernel (T = L < 64: the tile is the whole lattice): one union-find entry per site, bonds merged one by one.
-__global__ void __launch_bounds__(256) k_sw_tile(const SwArgs a, int T, int tiles_x, int tiles_per_replica, int n_sites) {
-    __shared__ int lab[SW_TILE * SW_TILE];
-    __shared__ uint32_t stage[SW_TILE + 1][2][2];  // [local row][colour][own word, word of the column right of the tile]
-    const int L = a.L, W = a.W;
-    const int r = blockIdx.x / tiles_per_replica, tile = blockIdx.x - r * tiles_per_replica;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int x0 = tx * T, y0 = ty * T;
-    const uint32_t *pl = a.planes + (size_t)r * 2 * L * W;
-    const int w0 = x0 >> 6, w1 = ((x0 + T) & (L - 1)) >> 6;
-    for (int k = threadIdx.x; k < (T + 1) * 4; k += blockDim.x) {
-        const int ly = k >> 2, c = (k >> 1) & 1, which = k & 1;
-        const int y = (y0 + ly) & (L - 1);
-        stage[ly][c][which] = pl[((size_t)c * L + y) * W + (which ? w1 : w0)];
-    }
-    const int n_tile = T * T, lt = ilog2(T);
-    for (int s = threadIdx.x; s < n_tile; s += blockDim.x) lab[s] = s;
-    __syncthreads();
-    const uint32_t anti = a.anti[r] & 1u, TP = a.TP[r];
-    const unsigned long long t = *a.d_t + a.t_off;
-    const uint32_t replica = a.replica_base + (uint32_t)r;
-    auto spin = [&](int lx, int ly) -> uint32_t {  // lx in [0, T], ly in [0, T]
-        const int x = (x0 + lx) & (L - 1), y = y0 + ly;  // parity of y0 + ly equals the parity of the wrapped row
-        const int c = (x + y) & 1, xh = x >> 1;
-        return (stage[ly][c][lx == T ? 1 : 0] >> (xh & 31)) & 1u;
-    };
-    for (int s = threadIdx.x; s < n_tile; s += blockDim.x) {
-        const int ly = s >> lt, lx = s & (T - 1);
-        const uint32_t me = spin(lx, ly);
-        const bool sat_r = lx + 1 < T && ((me ^ spin(lx + 1, ly) ^ anti) == 0u);
-        const bool sat_d = ly + 1 < T && ((me ^ spin(lx, ly + 1) ^ anti) == 0u);
-        if (!sat_r && !sat_d) continue;
-        const int i = (y0 + ly) * L + (x0 + lx);
-        const U4 u = philox_keyed(a.seed, (uint32_t)i, replica, t, PURPOSE_SW_BOND, 0);
-        if (sat_r && u.x < TP) sw_unite_smem(lab, s, s + 1);
-        if (sat_d && u.y < TP) sw_unite_smem(lab, s, s + T);
-    }
-    __syncthreads();
-    int *parent = a.parent + (size_t)r * n_sites;
-    for (int s = threadIdx.x; s < n_tile; s += blockDim.x) {
-        const int root = sw_find_smem(lab, s);
-        const int ly = s >> lt, lx = s & (T - 1), ry = root >> lt, rx = root & (T - 1);
-        parent[(y0 + ly) * L + (x0 + lx)] = (y0 + ry) * L + (x0 + rx);
-    }
-}
-
-// Border phase: the +x bonds of every tile's last column and the +y bonds of every tile's last row (periodic), merged in
-// global memory with the lock-free union-find above.  One thread per border site and direction.
-__global__ void __launch_bounds__(256) k_sw_border(const SwArgs a, int T, size_t n_threads, int n_sites) {
-    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (idx >= n_threads) return;
-    const int L = a.L, W = a.W, ll = ilog2(L), lnt = ll - ilog2(T);  // L / T tiles per direction, all powers of two
-    const size_t r = idx >> (ll + lnt + 1);
-    uint32_t k = (uint32_t)(idx & (((size_t)1 << (ll + lnt + 1)) - 1));
-    const int dir = (int)(k >> (ll + lnt));  // 0: +x bond of a last-column site, 1: +y bond of a last-row site
-    k &= (1u << (ll + lnt)) - 1u;
-    const int along = (int)(k & (uint32_t)(L - 1)), blk = (int)(k >> ll);
-    const int x = dir ? along : blk * T + T - 1, y = dir ? blk * T + T - 1 : along;
-    const int xn = dir ? x : (x + 1) & (L - 1), yn = dir ? (y + 1) & (L - 1) : y;
-    const uint32_t *pl = a.planes + r * 2 * (size_t)L * W;
-    if ((sw_spin_bit(pl, L, W, x, y) ^ sw_spin_bit(pl, L, W, xn, yn) ^ (a.anti[r] & 1u)) != 0u) return;
-    const int i = y * L + x;
-    const U4 u = philox_keyed(a.seed, (uint32_t)i, a.replica_base + (uint32_t)r, *a.d_t + a.t_off, PURPOSE_SW_BOND, 0);
-    if ((dir ? u.y : u.x) < a.TP[r]) sw_unite(a.parent + r * (size_t)n_sites, i, yn * L + xn);
-}
-
-// After the border merges a tile-local root may sit at the bottom of a long chain of hooks (one per tile the cluster
-// crosses).  Every local root that can have been hooked owns an end point of a border bond, so one thread per border
-// bond points the local roots of both end points straight at their final root; k_sw_flip then needs two hops per site.
-__global__ void __launch_bounds__(256) k_sw_border_compress(const SwArgs a, int T, size_t n_threads, int n_sites) {
-    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (idx >= n_threads) return;
-    const int L = a.L, ll = ilog2(L), lnt = ll - ilog2(T);
-    const size_t r = idx >> (ll + lnt + 1);
-    uint32_t k = (uint32_t)(idx & (((size_t)1 << (ll + lnt + 1)) - 1));
-    const int dir = (int)(k >> (ll + lnt));
-    k &= (1u << (ll + lnt)) - 1u;
-    const int along = (int)(k & (uint32_t)(L - 1)), blk = (int)(k >> ll);
-    const int x = dir ? along : blk * T + T - 1, y = dir ? blk * T + T - 1 : along;
-    const int xn = dir ? x : (x + 1) & (L - 1), yn = dir ? (y + 1) & (L - 1) : y;
-    int *parent = a.parent + r * (size_t)n_sites;
-    const int ends[2] = {y * L + x, yn * L + xn};
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const int loc = __ldcg(parent + ends[e]);  // the tile-local root (or already the final one)
-        const int root = sw_find(parent, loc);
-        if (root != loc) __stcg(parent + loc, root);
-    }
-}
-
-// coin bitmap: bit i of a replica's map = coin of the cluster whose root is site i (used only where i is a root).
-// One Philox call yields the coins of 128 consecutive site indices; one thread per call.
-__global__ void __launch_bounds__(256) k_sw_coins(const SwArgs a, size_t n_calls, int calls_per_replica) {
-    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (idx >= n_calls) return;
-    const size_t r = idx / (size_t)calls_per_replica;
-    const uint32_t g = (uint32_t)(idx - r * (size_t)calls_per_replica);
-    const U4 u = philox_keyed(a.seed, g, a.replica_base + (uint32_t)r, *a.d_t + a.t_off, PURPOSE_SW_FLIP, 0);
-    reinterpret_cast<uint4 *>(a.coins)[idx] = make_uint4(u.x, u.y, u.z, u.w);
-}
-
-__global__ void __launch_bounds__(256) k_sw_flip(const SwArgs a, size_t n_warps, int n_sites, int calls_per_replica) {
-    const SwSite s = sw_site(a, n_warps);
-    bool flip = false;
-    if (s.active) {
-        const uint32_t root = (uint32_t)sw_find(a.parent + s.r * (size_t)n_sites, s.i);
-        flip = (a.coins[s.r * (size_t)calls_per_replica * 4 + (root >> 5)] >> (root & 31u)) & 1u;
-    }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, flip);
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    if (s.lane == 0 && warp < n_warps && m) a.planes[(s.r * 2 + s.c) * (size_t)a.L * a.W + (size_t)s.y * a.W + s.w] ^= m;
-}
-
-// ---- RGNN (rgnn.cpp:281-339): scalar output of the b=2 filter pyramid and its central-difference gradient ---------
-// One thread per (replica, variant): variant 0 = W, variants 1..8 = W +- h on one weight (rgnn.cpp:321-331).  The
-// pyramid is walked depth-first in Morton order with a log2(L)-deep stack, in the oracle's operation order and with
-// explicit round-to-nearest multiplies/adds (no FMA contraction), so results equal the scalar code bit for bit.
-// W is column-major: W[k*2 + r] = W(r,k).  Internal coordinates: x = reference row i, y = reference column j.
-__device__ __forceinline__ double rgnn_block(const double W[4], double b00, double b10, double b01, double b11) {
-    // block(k,c): k = row offset (x), c = column offset (y); conv(r,c) = W(r,0) block(0,c) + W(r,1) block(1,c)
-    double l1 = 0.0;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const double x0 = c == 0 ? b00 : b01, x1 = c == 0 ? b10 : b11;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const double acc = __dadd_rn(__dmul_rn(W[0 * 2 + r], x0), __dmul_rn(W[1 * 2 + r], x1));
-            l1 = __dadd_rn(l1, fabs(acc));
-        }
-    }
-    return l1;
-}
-
-__device__ __forceinline__ double spin_at(const uint32_t *planes, int L, int W, int x, int y) {
-    const int c = (x + y) & 1, xh = x >> 1;
-    return ((planes[((size_t)c * L + y) * W + (xh >> 5)] >> (xh & 31)) & 1u) ? 1.0 : -1.0;
-}
-
-__global__ void __launch_bounds__(128) k_rgnn(const uint32_t *planes_all, int L, int n_replicas, const double *W_in, double h,
-                                              double *u_out, double *grad_out, double *acc, int accumulate) {
-    const int slot = threadIdx.x / 9, v = threadIdx.x - slot * 9;
-    const int r = threadIdx.x < 126 ? blockIdx.x * 14 + slot : n_replicas;  // threads 126, 127 idle
-    __shared__ double sh_u[128];
-    double u = 0.0;
-    if (r < n_replicas) {
-        double W[4] = {W_in[0], W_in[1], W_in[2], W_in[3]};
-        if (v > 0) {  // element e = (v-1)/2 in the order i outer, j inner of rgnn.cpp:318-319: (i,j) -> W[j*2+i]
-            const int e = (v - 1) >> 1, i = e >> 1, j = e & 1;
-            W[j * 2 + i] = (v & 1) ? __dadd_rn(W[j * 2 + i], h) : __dadd_rn(W[j * 2 + i], -h);
-        }
-        const uint32_t *planes = planes_all + (size_t)r * 2 * L * l0_words(L);
-        const int Wd = l0_words(L);
-        int depth = 0;
-        for (int n = L; n > 1; n >>= 1) ++depth;  // number of filter applications
-        // stack[level][slot]: results of the four children of the node being assembled at `level`
-        double stack[MAX_LEVELS][4];
-        int cnt[MAX_LEVELS];
-        for (int l = 0; l < depth; ++l) cnt[l] = 0;
-        const int n_blocks = (L / 2) * (L / 2);
-        for (int m = 0; m < n_blocks; ++m) {
-            // Morton decode: block (bi, bj) at the first level, bi from the even bits, bj from the odd bits
-            int bi = 0, bj = 0;
-            for (int k = 0; k < depth - 1; ++k) {
-                bi |= ((m >> (2 * k)) & 1) << k;
-                bj |= ((m >> (2 * k + 1)) & 1) << k;
-            }
-            double val = rgnn_block(W, spin_at(planes, L, Wd, 2 * bi, 2 * bj), spin_at(planes, L, Wd, 2 * bi + 1, 2 * bj),
-                                    spin_at(planes, L, Wd, 2 * bi, 2 * bj + 1), spin_at(planes, L, Wd, 2 * bi + 1, 2 * bj + 1));
-            // push upwards: child slot = (k offset, c offset) = (bi & 1, bj & 1) at each level
-            int lvl = 1, ci = bi, cj = bj;
-            while (lvl < depth) {
-                stack[lvl][(cj & 1) * 2 + (ci & 1)] = val;
-                if (++cnt[lvl] < 4) break;
-                cnt[lvl] = 0;
-                val = rgnn_block(W, stack[lvl][0], stack[lvl][1], stack[lvl][2], stack[lvl][3]);
-                ci >>= 1;
-                cj >>= 1;
-                ++lvl;
-            }
-            if (lvl == depth) u = val;
-        }
-    }
-    sh_u[threadIdx.x] = u;
-    __syncthreads();
-    // variant 0 of each replica gathers its 8 neighbours (same block: 128 is not a multiple of 9, so guard the edge
-    // by recomputing nothing — blocks are sized in whole replicas by the launcher: 126 = 14 * 9 threads are used)
-    if (r < n_replicas && v == 0) {
-        const double *uu = &sh_u[threadIdx.x];
-        const double inv2h = 2.0 * h;
-        double g[4];
-        for (int e = 0; e < 4; ++e) g[e] = __ddiv_rn(__dadd_rn(uu[1 + 2 * e], -uu[2 + 2 * e]), inv2h);  // (out1-out2)/(2h)
-        // g[e] with e = i*2 + j  ->  column-major grad[j*2 + i]
-        if (u_out) u_out[r] = uu[0];
-        if (grad_out)
-            for (int i = 0; i < 2; ++i)
-                for (int j = 0; j < 2; ++j) grad_out[(size_t)r * 4 + j * 2 + i] = g[i * 2 + j];
-        if (accumulate) {
-            double *a = acc + (size_t)r * 6;
-            a[0] = __dadd_rn(a[0], uu[0]);
-            a[1] = __dadd_rn(a[1], __dmul_rn(uu[0], uu[0]));
-            for (int i = 0; i < 2; ++i)
-                for (int j = 0; j < 2; ++j) a[2 + j * 2 + i] = __dadd_rn(a[2 + j * 2 + i], g[i * 2 + j]);
-        }
-    }
-}
-
-__global__ void k_advance_t(unsigned long long *d_t, unsigned long long by) { *d_t += by; }
-
-__global__ void k_init_hot(uint32_t *planes, int L, int W, int bits, size_t n_words, uint64_t seed, uint32_t replica_base) {
-    const size_t per = (size_t)2 * L * W;
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n_words; idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(idx / per);
-        const uint32_t word_id = (uint32_t)(idx - (size_t)r * per);
-        planes[idx] = philox_keyed(seed, word_id, replica_base + r, 0ull, PURPOSE_INIT, 0).x & valid_mask(bits);
-    }
-}
-
-__global__ void k_fill(uint32_t *p, size_t n, uint32_t v) {
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) p[idx] = v;
-}
-
-// int32 column-major (an internal row is contiguous) -> colour planes.  One warp per (replica, row, word):
-// lane l owns x = 64w+2l (even) and x+1 (odd); two ballots give the two colour words of that row.
-__global__ void k_pack0(const int32_t *spins, uint32_t *planes, int L, int W, size_t n_warps) {
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_warps) return;
-    const int w = (int)(warp % W);
-    const size_t ry = warp / W;
-    const int y = (int)(ry % L);
-    const size_t r = ry / L;
-    const int x = 64 * w + 2 * lane;
-    int2 v = make_int2(0, 0);
-    if (x < L) v = *reinterpret_cast<const int2 *>(spins + (r * L + y) * (size_t)L + x);
-    const uint32_t even = __ballot_sync(0xFFFFFFFFu, v.x > 0), odd = __ballot_sync(0xFFFFFFFFu, v.y > 0);
-    if (lane == 0) {
-        const int ce = y & 1;  // plane whose row offset is 0 holds the even-x sites
-        planes[((r * 2 + ce) * L + y) * W + w] = even;
-        planes[((r * 2 + (1 - ce)) * L + y) * W + w] = odd;
-    }
-}
-
-// packed natural transport format (hostpack.cpp: row y, bit x, max(1, L/32) words per row) -> colour planes.
-// One thread per (replica, row, colour-plane word w): the word's 32 sites x = 2x'+par come from natural words 2w, 2w+1.
-__global__ void k_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int W, int bits, size_t n) {
-    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const int w = (int)(idx % W);
-    const size_t ry = idx / W;
-    const int y = (int)(ry % L);
-    const size_t r = ry / L;
-    const int Wn = nat_words(L);
-    const uint32_t *row = nat + (r * L + y) * (size_t)Wn;
-    uint32_t even, odd;
-    if (Wn == 1) {
-        even = compress_even(row[0]);
-        odd = compress_even(row[0] >> 1);
-    } else {
-        const uint32_t a = row[2 * w], b = row[2 * w + 1];
-        even = compress_even(a) | (compress_even(b) << 16);
-        odd = compress_even(a >> 1) | (compress_even(b >> 1) << 16);
-    }
-    const uint32_t mask = valid_mask(bits);
-    const int ce = y & 1;  // plane whose row offset is 0 holds the even-x sites
-    planes[((r * 2 + ce) * L + y) * W + w] = even & mask;
-    planes[((r * 2 + (1 - ce)) * L + y) * W + w] = odd & mask;
-}
-
-__global__ void k_unpack0(const uint32_t *planes, int32_t *spins, int L, int W, size_t n_warps) {
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_warps) return;
-    const int w = (int)(warp % W);
-    const size_t ry = warp / W;
-    const int y = (int)(ry % L);
-    const size_t r = ry / L;
-    const int ce = y & 1;
-    const uint32_t even = planes[((r * 2 + ce) * L + y) * W + w], odd = planes[((r * 2 + (1 - ce)) * L + y) * W + w];
-    const int x = 64 * w + 2 * lane;
-    if (x < L) {
-        int2 v;
-        v.x = ((even >> lane) & 1u) ? 1 : -1;
-        v.y = ((odd >> lane) & 1u) ? 1 : -1;
-        *reinterpret_cast<int2 *>(spins + (r * L + y) * (size_t)L + x) = v;
-    }
-}
-
-__global__ void k_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int Wn, size_t n_warps) {
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_warps) return;
-    const uint32_t word = lev[warp];
-    const int w = (int)(warp % Wn);
-    const size_t ry = warp / Wn;
-    const int x = 32 * w + lane;
-    if (x < Ln) spins[ry * (size_t)Ln + x] = ((word >> lane) & 1u) ? 1 : -1;
-}
-
-// totals over (replica, bin) of every slot, as four 32-bit limbs in int64 (top limb signed)
-__global__ void k_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= N_SLOTS) return;
-    __int128 tot = 0;
-    for (int k = 0; k < n_rb; ++k) {
-        const size_t i = (size_t)k * N_SLOTS + slot;
-        tot += ((__int128)hi[i] << 64) | (__int128)lo[i];
-    }
-    const unsigned long long tl = (unsigned long long)tot;
-    const long long th = (long long)(tot >> 64);
-    out[4 * slot + 0] = (long long)(tl & 0xFFFFFFFFull);
-    out[4 * slot + 1] = (long long)(tl >> 32);
-    out[4 * slot + 2] = (long long)((unsigned long long)th & 0xFFFFFFFFull);
-    out[4 * slot + 3] = th >> 32;
-}
-
 int g_max_smem = -1;
 
 }  // namespace
@@ -1342,21 +801,6 @@ int sweep0_max_smem() {
 }
 
 
-void launch_sw_update(const SwArgs &a, int n_replicas, cudaStream_t st) {
-    const size_t n_sites = (size_t)a.L * a.L;
-    const int T = a.L < SW_TILE ? a.L : SW_TILE, tiles_x = a.L / T, tiles = tiles_x * tiles_x;
-    if (T == SW_TILE) k_sw_tile64<<<(unsigned)(n_replicas * tiles), 256, 0, st>>>(a, tiles_x, tiles, (int)n_sites);
-    else k_sw_tile<<<(unsigned)(n_replicas * tiles), 256, 0, st>>>(a, T, tiles_x, tiles, (int)n_sites);
-    const size_t n_border = (size_t)n_replicas * 2 * a.L * tiles_x;
-    k_sw_border<<<(unsigned)((n_border + 255) / 256), 256, 0, st>>>(a, T, n_border, (int)n_sites);
-    k_sw_border_compress<<<(unsigned)((n_border + 255) / 256), 256, 0, st>>>(a, T, n_border, (int)n_sites);
-    const int calls_per_replica = (int)((n_sites + 127) / 128);
-    const size_t n_calls = (size_t)n_replicas * calls_per_replica;
-    k_sw_coins<<<(unsigned)((n_calls + 255) / 256), 256, 0, st>>>(a, n_calls, calls_per_replica);
-    const size_t n_warps = (size_t)n_replicas * 2 * a.L * a.W;
-    k_sw_flip<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(a, n_warps, (int)n_sites, calls_per_replica);
-}
-
 void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st) {
     sweep0_max_smem();
     const int threads = sweep0_threads(a.L, a.L - 2, 2);  // (L+2) rows of W words
@@ -1383,55 +827,5 @@ void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st) {
 }
 
 void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st) { k_tail<<<n_replicas, 256, 0, st>>>(a); }
-
-void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st) {
-    k_total_limbs<<<(N_SLOTS + 127) / 128, 128, 0, st>>>(lo, hi, n_rb, out);
-}
-
-void launch_rgnn(const uint32_t *planes, int L, int n_replicas, const double *W, double h, double *u_out, double *grad_out,
-                 double *acc, int accumulate, cudaStream_t st) {
-    // 14 replicas x 9 variants = 126 of the 128 threads of a block: a replica never straddles two blocks
-    const int blocks = (n_replicas + 13) / 14;
-    k_rgnn<<<blocks, 128, 0, st>>>(planes, L, n_replicas, W, h, u_out, grad_out, acc, accumulate);
-}
-
-void launch_advance_t(unsigned long long *d_t, unsigned long long by, cudaStream_t st) { k_advance_t<<<1, 1, 0, st>>>(d_t, by); }
-
-void launch_init_hot(uint32_t *planes, int L, int n_replicas, uint64_t seed, uint32_t replica_base, cudaStream_t st) {
-    const int W = l0_words(L);
-    const size_t n = (size_t)n_replicas * 2 * L * W;
-    const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
-    k_init_hot<<<blocks, 256, 0, st>>>(planes, L, W, l0_bits(L), n, seed, replica_base);
-}
-
-void launch_init_cold(uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
-    const size_t n = (size_t)n_replicas * 2 * L * l0_words(L);
-    const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
-    k_fill<<<blocks, 256, 0, st>>>(planes, n, valid_mask(l0_bits(L)));
-}
-
-void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
-    const int W = l0_words(L);
-    const size_t n_warps = (size_t)n_replicas * L * W;
-    k_pack0<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(spins, planes, L, W, n_warps);
-}
-
-void launch_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
-    const int W = l0_words(L);
-    const size_t n = (size_t)n_replicas * L * W;
-    k_pack_nat<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nat, planes, L, W, l0_bits(L), n);
-}
-
-void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st) {
-    const int W = l0_words(L);
-    const size_t n_warps = (size_t)n_replicas * L * W;
-    k_unpack0<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(planes, spins, L, W, n_warps);
-}
-
-void launch_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int n_replicas, cudaStream_t st) {
-    const int Wn = nat_words(Ln);
-    const size_t n_warps = (size_t)n_replicas * Ln * Wn;
-    k_unpackN<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(lev, spins, Ln, Wn, n_warps);
-}
 
 }  // namespace mcrg

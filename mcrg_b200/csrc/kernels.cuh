@@ -7,6 +7,10 @@
 
 namespace mcrg {
 
+#if defined(__CUDACC__)
+__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }  // v a power of two
+#endif
+
 constexpr int MAX_LEVELS = 15;          // L <= 2^15; levels 0..14 at most
 constexpr int NOP = 3;                  // even operators: nn, nnn, plaquette
 constexpr int TAIL_MAX_L = 256;         // blocked lattices up to this size finish inside one CTA's shared memory

@@ -1,0 +1,163 @@
+// Small kernels around the hot path: initial states, format conversion at the boundary (the reference's int32 column-major
+// imat <-> colour planes), sweep-counter bookkeeping, exact accumulator totals for the all-reduce.
+#include "kernels.cuh"
+
+namespace mcrg {
+
+namespace {
+
+__global__ void k_advance_t(unsigned long long *d_t, unsigned long long by) { *d_t += by; }
+
+__global__ void k_init_hot(uint32_t *planes, int L, int W, int bits, size_t n_words, uint64_t seed, uint32_t replica_base) {
+    const size_t per = (size_t)2 * L * W;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n_words; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(idx / per);
+        const uint32_t word_id = (uint32_t)(idx - (size_t)r * per);
+        planes[idx] = philox_keyed(seed, word_id, replica_base + r, 0ull, PURPOSE_INIT, 0).x & valid_mask(bits);
+    }
+}
+
+__global__ void k_fill(uint32_t *p, size_t n, uint32_t v) {
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) p[idx] = v;
+}
+
+// int32 column-major (an internal row is contiguous) -> colour planes.  One warp per (replica, row, word):
+// lane l owns x = 64w+2l (even) and x+1 (odd); two ballots give the two colour words of that row.
+__global__ void k_pack0(const int32_t *spins, uint32_t *planes, int L, int W, size_t n_warps) {
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_warps) return;
+    const int w = (int)(warp % W);
+    const size_t ry = warp / W;
+    const int y = (int)(ry % L);
+    const size_t r = ry / L;
+    const int x = 64 * w + 2 * lane;
+    int2 v = make_int2(0, 0);
+    if (x < L) v = *reinterpret_cast<const int2 *>(spins + (r * L + y) * (size_t)L + x);
+    const uint32_t even = __ballot_sync(0xFFFFFFFFu, v.x > 0), odd = __ballot_sync(0xFFFFFFFFu, v.y > 0);
+    if (lane == 0) {
+        const int ce = y & 1;  // plane whose row offset is 0 holds the even-x sites
+        planes[((r * 2 + ce) * L + y) * W + w] = even;
+        planes[((r * 2 + (1 - ce)) * L + y) * W + w] = odd;
+    }
+}
+
+// packed natural transport format (hostpack.cpp: row y, bit x, max(1, L/32) words per row) -> colour planes.
+// One thread per (replica, row, colour-plane word w): the word's 32 sites x = 2x'+par come from natural words 2w, 2w+1.
+__global__ void k_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int W, int bits, size_t n) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int w = (int)(idx % W);
+    const size_t ry = idx / W;
+    const int y = (int)(ry % L);
+    const size_t r = ry / L;
+    const int Wn = nat_words(L);
+    const uint32_t *row = nat + (r * L + y) * (size_t)Wn;
+    uint32_t even, odd;
+    if (Wn == 1) {
+        even = compress_even(row[0]);
+        odd = compress_even(row[0] >> 1);
+    } else {
+        const uint32_t a = row[2 * w], b = row[2 * w + 1];
+        even = compress_even(a) | (compress_even(b) << 16);
+        odd = compress_even(a >> 1) | (compress_even(b >> 1) << 16);
+    }
+    const uint32_t mask = valid_mask(bits);
+    const int ce = y & 1;  // plane whose row offset is 0 holds the even-x sites
+    planes[((r * 2 + ce) * L + y) * W + w] = even & mask;
+    planes[((r * 2 + (1 - ce)) * L + y) * W + w] = odd & mask;
+}
+
+__global__ void k_unpack0(const uint32_t *planes, int32_t *spins, int L, int W, size_t n_warps) {
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_warps) return;
+    const int w = (int)(warp % W);
+    const size_t ry = warp / W;
+    const int y = (int)(ry % L);
+    const size_t r = ry / L;
+    const int ce = y & 1;
+    const uint32_t even = planes[((r * 2 + ce) * L + y) * W + w], odd = planes[((r * 2 + (1 - ce)) * L + y) * W + w];
+    const int x = 64 * w + 2 * lane;
+    if (x < L) {
+        int2 v;
+        v.x = ((even >> lane) & 1u) ? 1 : -1;
+        v.y = ((odd >> lane) & 1u) ? 1 : -1;
+        *reinterpret_cast<int2 *>(spins + (r * L + y) * (size_t)L + x) = v;
+    }
+}
+
+__global__ void k_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int Wn, size_t n_warps) {
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_warps) return;
+    const uint32_t word = lev[warp];
+    const int w = (int)(warp % Wn);
+    const size_t ry = warp / Wn;
+    const int x = 32 * w + lane;
+    if (x < Ln) spins[ry * (size_t)Ln + x] = ((word >> lane) & 1u) ? 1 : -1;
+}
+
+// totals over (replica, bin) of every slot, as four 32-bit limbs in int64 (top limb signed)
+__global__ void k_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= N_SLOTS) return;
+    __int128 tot = 0;
+    for (int k = 0; k < n_rb; ++k) {
+        const size_t i = (size_t)k * N_SLOTS + slot;
+        tot += ((__int128)hi[i] << 64) | (__int128)lo[i];
+    }
+    const unsigned long long tl = (unsigned long long)tot;
+    const long long th = (long long)(tot >> 64);
+    out[4 * slot + 0] = (long long)(tl & 0xFFFFFFFFull);
+    out[4 * slot + 1] = (long long)(tl >> 32);
+    out[4 * slot + 2] = (long long)((unsigned long long)th & 0xFFFFFFFFull);
+    out[4 * slot + 3] = th >> 32;
+}
+
+}  // namespace
+
+void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st) {
+    k_total_limbs<<<(N_SLOTS + 127) / 128, 128, 0, st>>>(lo, hi, n_rb, out);
+}
+
+void launch_advance_t(unsigned long long *d_t, unsigned long long by, cudaStream_t st) { k_advance_t<<<1, 1, 0, st>>>(d_t, by); }
+
+void launch_init_hot(uint32_t *planes, int L, int n_replicas, uint64_t seed, uint32_t replica_base, cudaStream_t st) {
+    const int W = l0_words(L);
+    const size_t n = (size_t)n_replicas * 2 * L * W;
+    const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+    k_init_hot<<<blocks, 256, 0, st>>>(planes, L, W, l0_bits(L), n, seed, replica_base);
+}
+
+void launch_init_cold(uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
+    const size_t n = (size_t)n_replicas * 2 * L * l0_words(L);
+    const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+    k_fill<<<blocks, 256, 0, st>>>(planes, n, valid_mask(l0_bits(L)));
+}
+
+void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
+    const int W = l0_words(L);
+    const size_t n_warps = (size_t)n_replicas * L * W;
+    k_pack0<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(spins, planes, L, W, n_warps);
+}
+
+void launch_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int n_replicas, cudaStream_t st) {
+    const int W = l0_words(L);
+    const size_t n = (size_t)n_replicas * L * W;
+    k_pack_nat<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nat, planes, L, W, l0_bits(L), n);
+}
+
+void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st) {
+    const int W = l0_words(L);
+    const size_t n_warps = (size_t)n_replicas * L * W;
+    k_unpack0<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(planes, spins, L, W, n_warps);
+}
+
+void launch_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int n_replicas, cudaStream_t st) {
+    const int Wn = nat_words(Ln);
+    const size_t n_warps = (size_t)n_replicas * Ln * Wn;
+    k_unpackN<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(lev, spins, Ln, Wn, n_warps);
+}
+
+}  // namespace mcrg

@@ -44,8 +44,12 @@ def phase_summary(tag):
     tot_s, tot_e = sum(int(r[iN]) for r in data), sum(int(r[iE]) for r in data)
     bars = [k for k, r in enumerate(data) if "BAR.SYNC" in r[iS]]
     edges = [0] + [b + 1 for b in bars] + [len(data)]
-    names = ["stage (cp.async global->shared) + setup", "measure (level-0 correlators, block to level 1)",
-             "half-sweeps (pass 1 + queue pass 2; barriers between them are inside)", "(barrier tail)", "store"]
+    # k_sweep0 as of r1_final: barrier after the mbarrier init, after the strip has landed, after the measurement,
+    # after every half-sweep (folded into one region here: they sit inside inlined copies of the same function), ...
+    names = ["setup + mbarrier init", "TMA issue, threshold table, wait for the strip (mbarrier)",
+             "measure (level-0 correlators, block to level 1)",
+             "half-sweeps (pass 1 + queue pass 2; the barriers between them are inside)", "(barrier tail of the last half-sweep)",
+             "fence.proxy.async + TMA bulk store", "exit"]
     out = []
     for k, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
         seg = data[a:b]
