@@ -1,3 +1,4 @@
+# Run with gpurun --gpus 8: bench.py under torchrun at 8, 4, 2 GPUs of one box, then 1 GPU; outputs in gpurun_out/.
 for n in 8 4 2; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 8 --warmup 3 > gpurun_out/bench_n${n}_final.json 2> gpurun_out/bench_n${n}_final.err
   echo "rc=$?"; python -c "
