@@ -463,3 +463,57 @@ def test_rgnn_run_accumulates_like_the_reference_loop(mc):
             want[1] += u * u
             want[2:] += g
         assert np.array_equal(sums[r], want), (r, sums[r], want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# resume and sharding: results depend only on (seed, global replica id, sweep counter)
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("L,update", [(64, "metropolis"), (1024, "metropolis"), (128, "cluster")])
+def test_checkpoint_resume_reproduces_the_trajectory(mc, L, update):
+    """A checkpoint is (configurations in the reference layout, sweep counter): a fresh context restored from it
+    continues bit-identically — the counter-based RNG has no other state (checkpoint/resume)."""
+    seed, base = 99, 11
+    with mc.Context(L, 2, seed=seed, replica_base=base) as ctx:
+        ctx.set_update(update)
+        ctx.set_couplings([KC, -0.45])
+        ctx.init_hot()
+        ctx.sweep(7)
+        want = ctx.get_spins()
+        S_want = ctx.measure()
+    with mc.Context(L, 2, seed=seed, replica_base=base) as ctx:
+        ctx.set_update(update)
+        ctx.set_couplings([KC, -0.45])
+        ctx.init_hot()
+        ctx.sweep(3)
+        ckpt, t = ctx.get_spins(), ctx.sweep_counter
+    with mc.Context(L, 2, seed=seed, replica_base=base) as ctx:  # "restart"
+        ctx.set_update(update)
+        ctx.set_couplings([KC, -0.45])
+        ctx.set_spins(ckpt)
+        ctx.sweep_counter = t
+        ctx.sweep(4)
+        assert np.array_equal(ctx.get_spins(), want)
+        assert np.array_equal(ctx.measure(), S_want)
+
+
+def test_sharded_contexts_give_the_totals_of_one_context(mc):
+    """The multi-GPU layout on one device: 6 replicas in one context == 2 + 4 replicas in two contexts with
+    replica_base 0 and 2; accumulator totals (as the all-reduce would form them) are identical integers."""
+    L, seed, n_samples = 128, 31, 9
+    Ks = [KC, -0.43, -0.45, -0.47, -0.44, -0.42]
+
+    def totals(first, count):
+        with mc.Context(L, count, seed=seed, replica_base=first) as ctx:
+            ctx.set_tuning(strip_rows=32)  # the strip kernel, as on the large lattices
+            ctx.set_couplings(Ks[first:first + count])
+            ctx.init_hot()
+            ctx.sweep(5)
+            ctx.run(n_samples, 2, -1, 0)
+            acc, _ = ctx.accumulators()
+            return acc[:, 0, :]
+
+    whole = totals(0, 6)
+    parts = np.concatenate([totals(0, 2), totals(2, 4)], axis=0)
+    assert (whole == parts).all()
+    assert [int(x) for x in whole.sum(axis=0)] == [int(x) for x in parts.sum(axis=0)]
