@@ -10,8 +10,8 @@ namespace {
 // clusters inside 64 x 64 tiles with a union-find in shared memory.  k_sw_border: merge across tile edges in global
 // memory.  Both use a lock-free union-find whose hooks always point from the larger to the smaller root (atomicMin), so
 // the final root of a cluster is its smallest site index whatever the interleaving — the result is bit-identical to the
-// scalar specification.  k_sw_flip (one lane per site, one warp per packed word): find the root, flip the site iff the
-// root's coin is set; the 32 decisions of a word are gathered with a ballot and applied with one XOR.
+// scalar specification.  k_sw_border_compress points every tile-local root at its final root, k_sw_coins draws the cluster
+// coins (128 per Philox call) and k_sw_flip flips the sites whose root's coin is set (ballots + one atomic XOR per word).
 __device__ __forceinline__ int sw_find(const int *parent, int x) {
     int p = __ldcg(parent + x);
     while (p != x) {
@@ -49,31 +49,6 @@ __device__ __forceinline__ void sw_unite(int *parent, int a, int b) {
         if (old == a) return;                      // a was still a root: done
         a = old;                                   // somebody hooked a first: continue from where it points now
     }
-}
-
-struct SwSite {
-    size_t r;
-    int c, y, w, lane, x, i;
-    bool active;
-};
-
-__device__ __forceinline__ SwSite sw_site(const SwArgs &a, size_t n_warps) {
-    SwSite s;
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    s.lane = threadIdx.x & 31;
-    s.active = warp < n_warps && s.lane < a.bits;
-    const size_t wq = warp < n_warps ? warp : 0;  // W and L are powers of two: shifts, not 64-bit divisions
-    const int lw = ilog2(a.W), ll = ilog2(a.L);
-    s.w = (int)(wq & (size_t)(a.W - 1));
-    const size_t ry = wq >> lw;
-    s.y = (int)(ry & (size_t)(a.L - 1));
-    const size_t rc = ry >> ll;
-    s.c = (int)(rc & 1);
-    s.r = rc >> 1;
-    s.x = 2 * (32 * s.w + s.lane) + ((s.y + s.c) & 1);
-    if (s.x >= a.L) s.x = 0, s.active = false;
-    s.i = s.y * a.L + s.x;
-    return s;
 }
 
 // spin of site (x, y) as a bit, from the colour planes of one replica in global memory
@@ -292,7 +267,12 @@ __global__ void __launch_bounds__(256) k_sw_border(const SwArgs a, int T, size_t
     if ((sw_spin_bit(pl, L, W, x, y) ^ sw_spin_bit(pl, L, W, xn, yn) ^ (a.anti[r] & 1u)) != 0u) return;
     const int i = y * L + x;
     const U4 u = philox_keyed(a.seed, (uint32_t)i, a.replica_base + (uint32_t)r, *a.d_t + a.t_off, PURPOSE_SW_BOND, 0);
-    if ((dir ? u.y : u.x) < a.TP[r]) sw_unite(a.parent + r * (size_t)n_sites, i, yn * L + xn);
+    if ((dir ? u.y : u.x) < a.TP[r]) {
+        // unite the tile-local roots, not the sites: the entries of the sites themselves then never lie on a search
+        // path, stay equal to their tile-local root, and k_sw_border_compress / k_sw_flip can rely on that
+        int *parent = a.parent + r * (size_t)n_sites;
+        sw_unite(parent, __ldcg(parent + i), __ldcg(parent + yn * L + xn));
+    }
 }
 
 // After the border merges a tile-local root may sit at the bottom of a long chain of hooks (one per tile the cluster
@@ -313,9 +293,14 @@ __global__ void __launch_bounds__(256) k_sw_border_compress(const SwArgs a, int 
     const int ends[2] = {y * L + x, yn * L + xn};
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        const int loc = __ldcg(parent + ends[e]);  // the tile-local root (or already the final one)
+        // parent[end point] is its tile-local root — or, when the end point IS a tile-local root that was hooked, already
+        // one of its ancestors: point both the end point and that node at the final root
+        const int loc = __ldcg(parent + ends[e]);
         const int root = sw_find(parent, loc);
-        if (root != loc) __stcg(parent + loc, root);
+        if (root != loc) {
+            __stcg(parent + loc, root);
+            __stcg(parent + ends[e], root);
+        }
     }
 }
 
@@ -330,16 +315,37 @@ __global__ void __launch_bounds__(256) k_sw_coins(const SwArgs a, size_t n_calls
     reinterpret_cast<uint4 *>(a.coins)[idx] = make_uint4(u.x, u.y, u.z, u.w);
 }
 
+// Flip pass.  One warp per 64 consecutive sites of a row (both colours): lane l owns x = 64w + 2l and x + 1, so the
+// parent[] entries are read as coalesced 8-byte pairs and every lane has two independent dependent-load chains in
+// flight.  After k_sw_border_compress every site is at most two hops from its root — site -> tile-local root -> root —
+// hence root = parent[parent[i]] without a search loop.  The coins of the 2 x 32 sites are gathered with two ballots
+// and applied to the two colour words with one fire-and-forget atomic XOR each (each word has exactly one owner).
 __global__ void __launch_bounds__(256) k_sw_flip(const SwArgs a, size_t n_warps, int n_sites, int calls_per_replica) {
-    const SwSite s = sw_site(a, n_warps);
-    bool flip = false;
-    if (s.active) {
-        const uint32_t root = (uint32_t)sw_find(a.parent + s.r * (size_t)n_sites, s.i);
-        flip = (a.coins[s.r * (size_t)calls_per_replica * 4 + (root >> 5)] >> (root & 31u)) & 1u;
-    }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, flip);
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    if (s.lane == 0 && warp < n_warps && m) a.planes[(s.r * 2 + s.c) * (size_t)a.L * a.W + (size_t)s.y * a.W + s.w] ^= m;
+    if (warp >= n_warps) return;  // whole warps leave together
+    const int lane = threadIdx.x & 31;
+    const int L = a.L, W = a.W, lw = ilog2(W), ll = ilog2(L);
+    const int w = (int)(warp & (size_t)(W - 1));
+    const size_t ry = warp >> lw;
+    const int y = (int)(ry & (size_t)(L - 1));
+    const size_t r = ry >> ll;
+    const int x = 64 * w + 2 * lane;
+    bool f0 = false, f1 = false;
+    if (x < L) {
+        const int *parent = a.parent + r * (size_t)n_sites;
+        const uint32_t *coins = a.coins + r * (size_t)calls_per_replica * 4;
+        const int2 p = __ldcs(reinterpret_cast<const int2 *>(parent + y * L + x));  // read once: streaming
+        const uint32_t r0 = (uint32_t)__ldg(parent + p.x), r1 = (uint32_t)__ldg(parent + p.y);
+        f0 = (__ldg(coins + (r0 >> 5)) >> (r0 & 31u)) & 1u;
+        f1 = (__ldg(coins + (r1 >> 5)) >> (r1 & 31u)) & 1u;
+    }
+    const uint32_t even = __ballot_sync(0xFFFFFFFFu, f0), odd = __ballot_sync(0xFFFFFFFFu, f1);
+    if (lane == 0) {
+        const int ce = y & 1;  // the plane whose row offset is 0 holds the even-x sites
+        uint32_t *pl = a.planes + r * 2 * (size_t)L * W;
+        if (even) atomicXor(pl + ((size_t)ce * L + y) * W + w, even);
+        if (odd) atomicXor(pl + ((size_t)(1 - ce) * L + y) * W + w, odd);
+    }
 }
 
 }  // namespace
@@ -355,7 +361,7 @@ void launch_sw_update(const SwArgs &a, int n_replicas, cudaStream_t st) {
     const int calls_per_replica = (int)((n_sites + 127) / 128);
     const size_t n_calls = (size_t)n_replicas * calls_per_replica;
     k_sw_coins<<<(unsigned)((n_calls + 255) / 256), 256, 0, st>>>(a, n_calls, calls_per_replica);
-    const size_t n_warps = (size_t)n_replicas * 2 * a.L * a.W;
+    const size_t n_warps = (size_t)n_replicas * a.L * a.W;  // one warp per 64 sites of a row
     k_sw_flip<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(a, n_warps, (int)n_sites, calls_per_replica);
 }
 
