@@ -257,6 +257,7 @@ def run_ours(args, rank, world, local_rank):
             return n_loc * L * L * sweeps / (best * 1e-3) / 1e9
 
         other = {"sweep_only": rate(lambda: ctx.sweep(32), 32), "m16": rate(lambda: ctx.run(4, 16, -1, 0), 64)}
+        philox_calls_per_s = ctx.probe_philox_rate()  # live: the instruction-issue ceiling of the update's arithmetic core
         barrier()
 
         # ---- end to end through the C ABI with host buffers
@@ -378,11 +379,13 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_SITE_DOMINANT * n_loc * L * L,
                      "kernel_ms": dom_ms, "kernel_share_of_sample": dom_ms / sample_ms if sample_ms > 0 else None,
                      "per_sample_ms": prof,
-                     "compute_bound": {"what": "Philox4x32-10 + 4-plane lazy compare, measured ceiling on this B200 "
-                                               "(profiles/microbench_pipes_r1.txt): 0.37 T calls/s; a sweep needs ~2.1 calls per 32 sites",
-                                       "ceiling_G_sites_per_s": 0.37e3 * 32 / 2.1,
+                     "compute_bound": {"what": "Philox4x32-10 + 4-plane lazy compare alone, measured live on this GPU by "
+                                               "mcrg_probe_philox_rate (see also profiles/microbench_pipes_r1.txt); a sweep needs ~2.1 "
+                                               "calls per 32 sites, so ceiling = calls/s * 32 / 2.1",
+                                       "philox_T_calls_per_s": philox_calls_per_s / 1e12,
+                                       "ceiling_G_sites_per_s": philox_calls_per_s / 1e9 * 32 / 2.1,
                                        "achieved_G_sites_per_s": n_loc * L * L / (dom_ms * 1e-3) / 1e9,
-                                       "frac": (n_loc * L * L / (dom_ms * 1e-3) / 1e9) / (0.37e3 * 32 / 2.1)},
+                                       "frac": (n_loc * L * L / (dom_ms * 1e-3)) / (philox_calls_per_s * 32 / 2.1)},
                      "note": "1 bit/spin makes the compulsory traffic tiny: the kernel is INT/Philox-issue bound, not HBM bound "
                              "(see DESIGN.md section 3.1 and profiles/)"},
     }

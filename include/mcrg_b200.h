@@ -122,6 +122,11 @@ int mcrg_run(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, int max_levels
  * tail kernel}.  The chain and the accumulators advance exactly as in mcrg_run. */
 int mcrg_profile_kernels(mcrg_ctx *ctx, int n_samples, int sweeps_per_sample, int max_levels, float out_ms[4]);
 
+/* Measurement aid for the roofline note: the measured rate (calls per second, whole device) of the arithmetic core of the
+ * Metropolis update — Philox4x32-10 + 4-plane lazy threshold compare, two independent calls in flight per thread — i.e. the
+ * instruction-issue ceiling a sweep (about 2.1 calls per 32 sites) can approach on this GPU at its current clocks. */
+int mcrg_probe_philox_rate(mcrg_ctx *ctx, double *calls_per_s);
+
 /* ---- RGNN: consumer of the sampler ---------------------------------------------------------- */
 /* RenormalizationGroupNeuralNetwork::set_weights (rgnn.cpp:38-42): W is the 2x2 filter, column-major (W[k*2+r] = W(r,k)) */
 int mcrg_rgnn_set_weights(mcrg_ctx *ctx, const double *W);

@@ -68,6 +68,7 @@ def lib():
         l.mcrg_observables.argtypes = [vp, vp, vp, vp, vp]
         l.mcrg_run.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         l.mcrg_profile_kernels.argtypes = [vp, C.c_int, C.c_int, C.c_int, P(C.c_float)]
+        l.mcrg_probe_philox_rate.argtypes = [vp, P(C.c_double)]
         l.mcrg_rgnn_set_weights.argtypes = [vp, vp]
         l.mcrg_rgnn_eval.argtypes = [vp, C.c_double, vp, vp]
         l.mcrg_rgnn_run.argtypes = [vp, C.c_int, C.c_int, C.c_double]
@@ -243,6 +244,12 @@ class Context:
         out = (C.c_float * 4)()
         _check(lib().mcrg_profile_kernels(self._h, n_samples, sweeps_per_sample, max_levels, out))
         return dict(sweep_measure=out[0], sweep_only=out[1], level=out[2], tail=out[3])
+
+    def probe_philox_rate(self):
+        """-> measured Philox4x32-10 + 4-plane compare calls per second on this device (instruction-issue ceiling)."""
+        v = C.c_double(0)
+        _check(lib().mcrg_probe_philox_rate(self._h, C.byref(v)))
+        return v.value
 
     # ---- RGNN
     def rgnn_set_weights(self, W):

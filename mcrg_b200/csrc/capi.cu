@@ -849,6 +849,14 @@ int mcrg_profile_kernels(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int 
     return 0;
 }
 
+int mcrg_probe_philox_rate(mcrg_ctx *c, double *calls_per_s) {
+    if (!c || !calls_per_s) return fail(MCRG_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (probe_philox_rate(c->stream, calls_per_s) != 0) return fail(MCRG_ERR_CUDA, "Philox throughput probe failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 int mcrg_rgnn_set_weights(mcrg_ctx *c, const double *W) {
     if (!c || !W) return fail(MCRG_ERR_ARG, "null pointer");
     CK(cudaSetDevice(c->device));

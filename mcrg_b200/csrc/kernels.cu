@@ -1,20 +1,25 @@
 // sm_100a kernels of the MCRG hot path (no tensor cores: nothing here is a contraction; the work is bitwise
 // integer + Philox, staged through shared memory, reduced with warp primitives and one atomic pass per CTA).
 //
-//   k_sweep0<MEASURE>  one strip of R rows of one replica: stage strip + halo in shared memory (128-bit loads),
+//   k_sweep0<MEASURE>  one strip of R rows of one replica: stage strip + halo in shared memory (TMA bulk copies +
+//                      mbarrier; plain loads for rows shorter than 16 bytes),
 //                      [MEASURE: level-0 correlator popcounts + b=2 majority block to level 1 (Philox ties)],
 //                      nsw full checkerboard Metropolis sweeps with halo recomputation (counter-based RNG makes
-//                      the redundant halo updates bit-identical to the owning strip's), store the strip.
+//                      the redundant halo updates bit-identical to the owning strip's), store the strip (TMA).
 //                      Replaces IsingModel::sample_new_configuration (ising.cpp:87-155, Wolff there, Metropolis
 //                      here per the north_star), Lattice::calc_interactions (lattice.cpp:102-120) and the first
 //                      block_spin_transformation (mcrg.cpp:314-348) of the sample loop mcrg.cpp:72-98.
 //   k_level            natural-layout level n: correlator popcounts + block to level n+1, strips of rows.
 //   k_tail             one CTA per replica: remaining (small) levels entirely in shared memory, then the
 //                      accumulation of mcrg.cpp:86-97 (S, S(n) x S(n-1), S(n) x S(n)) into exact 128-bit sums.
+//   k_resident         lattices up to 512^2: the whole replica, its pyramid and the accumulators of a block of samples
+//                      live in one CTA's shared memory; one launch per block of samples.
+// The cluster update, the RGNN kernels and the boundary/bookkeeping kernels are in cluster.cu, rgnn.cu, util_kernels.cu.
 #include "kernels.cuh"
 
 // 3 CTAs of 256 threads per SM = 80 registers per thread: the row body of mc_row keeps its constants in registers
-// (measured: 0.274 ms per launch of the headline configuration against 0.286 ms with 4 CTAs / 64 registers)
+// (measured with per-thread staging loads: 0.274 ms per launch of the headline configuration against 0.286 ms with
+// 4 CTAs / 64 registers; 0.260 ms today with TMA staging)
 #ifndef MCRG_SWEEP_MIN_BLOCKS
 #define MCRG_SWEEP_MIN_BLOCKS 3
 #endif
@@ -36,11 +41,6 @@ __device__ __forceinline__ void warp_reduce_to(const Counts &c, unsigned int *ce
         atomicAdd(&cells[3], u);
     }
 }
-
-// rows [row_lo, row_lo+nrows) of a [*, W] word array: global -> shared, periodic in y (L a power of two).
-// 16-byte asynchronous copies (cp.async.cg: L2 -> shared memory without a register round trip), so that every copy of
-// a thread is in flight at once; stage_wait() before the barrier that publishes the tile.
-__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 // ---- TMA bulk copies (cp.async.bulk, one instruction per contiguous run of rows) + mbarrier -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t bulk_stage_rows(uint32_t *dst, const uint32_
     return total;
 }
 
-// Staging entry points used by every kernel: TMA when the rows are 16-byte multiples, else cp.async / plain loads.
+// Staging entry points used by every kernel: TMA when the rows are 16-byte multiples (L >= 256), else plain loads.
 // Protocol: tile_stage_begin (all threads; contains a barrier when TMA is used), tile_stage_plane per plane with the SAME
 // total byte count announced up front, tile_stage_wait (all threads), then the caller's __syncthreads().
 __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W, int L);
@@ -114,27 +114,17 @@ __device__ __forceinline__ void tile_stage_plane(bool tma, unsigned long long *b
     }
 }
 __device__ __forceinline__ void tile_stage_wait(bool tma, unsigned long long *bar) {
-    if (tma) mbar_wait(bar, 0);
-    else stage_wait();
+    if (tma) mbar_wait(bar, 0);  // plain loads need nothing beyond the caller's barrier
 }
 
+// rows shorter than 16 bytes (W < 4, i.e. L < 256): plain 4-byte loads, periodic in y (L and W are powers of two)
 __device__ __forceinline__ void stage_rows(uint32_t *dst, const uint32_t *src_plane, int y_first, int nrows, int W,
                                            int L) {
-    if ((W & 3) == 0) {  // W is a power of two: shifts, not divisions
-        const int W4 = W >> 2, l4 = ilog2(W4), n4 = nrows << l4;
-        for (int idx = threadIdx.x; idx < n4; idx += blockDim.x) {
-            const int lr = idx >> l4, w4 = idx & (W4 - 1);
-            const int y = (y_first + lr) & (L - 1);
-            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint4 *>(dst) + idx);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(reinterpret_cast<const uint4 *>(src_plane + (size_t)y * W) + w4) : "memory");
-        }
-    } else {
-        const int lw = ilog2(W), n = nrows << lw;
-        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            const int lr = idx >> lw, w = idx & (W - 1);
-            const int y = (y_first + lr) & (L - 1);
-            dst[idx] = __ldg(src_plane + (size_t)y * W + w);
-        }
+    const int lw = ilog2(W), n = nrows << lw;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int lr = idx >> lw, w = idx & (W - 1);
+        const int y = (y_first + lr) & (L - 1);
+        dst[idx] = __ldg(src_plane + (size_t)y * W + w);
     }
 }
 
@@ -380,7 +370,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     s.L = L;
     s.y_first = (y0 - a.H) & (L - 1);
     const uint32_t *src_r = a.src + (size_t)r * 2 * L * W;
-    // staging: TMA bulk copies signalled through an mbarrier when rows are 16-byte multiples (L >= 256), else cp.async / loads
+    // staging: TMA bulk copies signalled through an mbarrier when rows are 16-byte multiples (L >= 256), else plain loads
     const bool tma = tile_stage_begin(&bar, W, 2u * (uint32_t)rows * (uint32_t)W * 4u);
     tile_stage_plane(tma, &bar, s0_plane(s, 0), src_r, s.y_first, rows, W, L);
     tile_stage_plane(tma, &bar, s0_plane(s, 1), src_r + (size_t)L * W, s.y_first, rows, W, L);

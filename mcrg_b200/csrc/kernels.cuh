@@ -144,6 +144,7 @@ void launch_pack0(const int32_t *spins, uint32_t *planes, int L, int n_replicas,
 void launch_pack_nat(const uint32_t *nat, uint32_t *planes, int L, int n_replicas, cudaStream_t st);
 void launch_unpack0(const uint32_t *planes, int32_t *spins, int L, int n_replicas, cudaStream_t st);
 void launch_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int n_replicas, cudaStream_t st);
+int probe_philox_rate(cudaStream_t st, double *calls_per_s);
 size_t sweep0_smem_bytes(int L, int R, int H);
 int sweep0_threads(int L, int R, int H);
 int sweep0_max_smem();

@@ -115,7 +115,57 @@ __global__ void k_total_limbs(const unsigned long long *lo, const long long *hi,
     out[4 * slot + 3] = th >> 32;
 }
 
+// Instruction-throughput probe for the roofline note of bench.py: the arithmetic core of the Metropolis row body and
+// nothing else — two interleaved Philox4x32-10 calls per step, each followed by the 4-plane lazy threshold compare with
+// the per-lane threshold select — on every SM with 8 warps per scheduler.  Reports Philox calls per second.
+__global__ void __launch_bounds__(256) k_probe_philox(uint32_t *out, uint64_t seed, int iters) {
+    __shared__ uint2 tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = make_uint2((threadIdx.x * 37u) & 1u ? ~0u : 0u, (threadIdx.x * 11u) & 2u ? ~0u : 0u);
+    __syncthreads();
+    uint32_t lt = 0, eq = 0xFFFFFFFFu;
+    const uint32_t sel = threadIdx.x * 2654435761u, w = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+        const U4 r0 = philox_keyed(seed, w, 7u, (uint64_t)i, PURPOSE_MC, 0), r1 = philox_keyed(seed, w, 7u, (uint64_t)i, PURPOSE_MC, 1);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint2 t = tab[(8 * i + e) & 31];
+            const uint32_t tm = (sel & t.x) | (~sel & t.y);
+            lt |= eq & ~rr[e] & tm;
+            eq &= ~(rr[e] ^ tm);
+        }
+        eq |= r0.x;  // keep lanes alive so that the compare is never skipped
+    }
+    out[w] = lt ^ eq;
+}
+
 }  // namespace
+
+int probe_philox_rate(cudaStream_t st, double *calls_per_s) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, iters = 2048;
+    uint32_t *out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * 256 * 4) != cudaSuccess) return -1;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    k_probe_philox<<<blocks, 256, 0, st>>>(out, 1234567ull, iters);  // warm-up
+    cudaEventRecord(a, st);
+    for (int k = 0; k < 3; ++k) k_probe_philox<<<blocks, 256, 0, st>>>(out, 1234567ull + k, iters);
+    cudaEventRecord(b, st);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    if (e != cudaSuccess || ms <= 0.f) return -1;
+    *calls_per_s = 3.0 * 2.0 * (double)blocks * 256.0 * iters / (ms * 1e-3);
+    return 0;
+}
 
 void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st) {
     k_total_limbs<<<(N_SLOTS + 127) / 128, 128, 0, st>>>(lo, hi, n_rb, out);
