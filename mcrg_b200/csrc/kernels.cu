@@ -23,6 +23,15 @@
 #ifndef MCRG_SWEEP_MIN_BLOCKS
 #define MCRG_SWEEP_MIN_BLOCKS 3
 #endif
+// k_level: 128 threads x 32 registers = 4096 registers per CTA, exactly what three resident sweep CTAs leave free on an
+// SM (65536 - 3 x 256 x 80), so the pyramid of sample s (side stream) shares SMs with the sweep of sample s+1 instead of
+// waiting for one of its CTA slots (measured: 36.8 -> 36.1 ms per 128-sample step)
+#ifndef MCRG_LEVEL_THREADS
+#define MCRG_LEVEL_THREADS 128
+#endif
+#ifndef MCRG_LEVEL_MIN_BLOCKS
+#define MCRG_LEVEL_MIN_BLOCKS 16
+#endif
 
 namespace mcrg {
 
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     }
 }
 
-__global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
+__global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_level(const LevelArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[4];
     __shared__ __align__(8) unsigned long long bar;
@@ -464,15 +473,22 @@ __global__ void __launch_bounds__(256) k_level(const LevelArgs a) {
         const int nb = (a.R >> 1) << lwb;
         TieCache coins;
         coins.init();
-        for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-            const int i = idx >> lwb, wb = idx & (Wb - 1);
-            uint32_t maj, tie;
-            block_pairN(s, 2 * i, wb, maj, tie);
-            const uint32_t q = (uint32_t)(((y0 >> 1) + i) << lwb) + (uint32_t)wb;
-            uint32_t o = maj;
-            if (tie) o |= tie & coins.get(a.seed, q, replica, t, a.level + 1);
-            out_r[q] = o;
-        }
+        // Output words q0 .. q0+nb-1, visited so that a thread does the four words that share one Philox call (q, q+256,
+        // q+512, q+768 inside a 1024-aligned chunk, see tie_group) back to back, whatever the block size.
+        const uint32_t q0 = (uint32_t)((y0 >> 1) << lwb), q1 = q0 + (uint32_t)nb;
+        for (uint32_t qc = q0 & ~1023u; qc < q1; qc += 1024u)
+            for (uint32_t p = threadIdx.x; p < 256u; p += blockDim.x)
+#pragma unroll
+                for (uint32_t e = 0; e < 4u; ++e) {
+                    const uint32_t q = qc + (e << 8) + p;
+                    if (q < q0 || q >= q1) continue;
+                    const int idx = (int)(q - q0), i = idx >> lwb, wb = idx & (Wb - 1);
+                    uint32_t maj, tie;
+                    block_pairN(s, 2 * i, wb, maj, tie);
+                    uint32_t o = maj;
+                    if (tie) o |= tie & coins.get(a.seed, q, replica, t, a.level + 1);
+                    out_r[q] = o;
+                }
     }
     warp_reduce_to(c, red);
     __syncthreads();
@@ -813,7 +829,7 @@ void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st) {
     const int Wn = nat_words(a.Ln);
     const size_t smem = (size_t)(a.R + 1) * Wn * sizeof(uint32_t);
     const dim3 grid(a.strips, n_replicas);
-    k_level<<<grid, pick_threads((long long)a.R * Wn, 256), smem, st>>>(a);
+    k_level<<<grid, pick_threads((long long)a.R * Wn, MCRG_LEVEL_THREADS), smem, st>>>(a);
 }
 
 void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st) { k_tail<<<n_replicas, 256, 0, st>>>(a); }
