@@ -162,6 +162,18 @@ int mcrg_accumulators_get(mcrg_ctx *ctx, int64_t *hi, uint64_t *lo, double *d);
  * DEVICE memory `dev_out` (4*n_slots int64) on the context's stream; pass it straight to the all-reduce. */
 int mcrg_accumulators_total_limbs_device(mcrg_ctx *ctx, void *dev_out);
 
+/* ---- several GPUs in one process ------------------------------------------------------------------------------
+ * Replaces `mpirun -n P` + the three MPI_Allreduce calls of mcrg.cpp:101-103 for C/C++ hosts.  Create one context per
+ * device (give each its own replica_base so that the chains differ), then mcrg_comm_init_all once; all the usual calls
+ * are asynchronous per context, so the devices work concurrently.  mcrg_allreduce_accumulators forms every device's
+ * limb totals, sums them with one ncclAllReduce(ncclInt64, ncclSum) per device (NVLink / NVSwitch) and returns the
+ * grand totals over all replicas and bins of all contexts as exact 128-bit integers hi/lo[n_slots] (either may be NULL).
+ * NCCL is dlopen'ed at mcrg_comm_init_all; the library does not depend on it otherwise.  (One process per GPU with
+ * torch.distributed, as bench.py does, needs none of this: use mcrg_accumulators_total_limbs_device.) */
+int mcrg_comm_init_all(int n, mcrg_ctx **ctxs);
+int mcrg_allreduce_accumulators(int n, mcrg_ctx **ctxs, int64_t *hi, uint64_t *lo);
+int mcrg_comm_destroy_all(int n, mcrg_ctx **ctxs);
+
 #ifdef __cplusplus
 }
 #endif

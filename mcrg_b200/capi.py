@@ -78,6 +78,9 @@ def lib():
         l.mcrg_accumulators_reset.argtypes = [vp]
         l.mcrg_accumulators_get.argtypes = [vp, vp, vp, vp]
         l.mcrg_accumulators_total_limbs_device.argtypes = [vp, vp]
+        l.mcrg_comm_init_all.argtypes = [C.c_int, P(vp)]
+        l.mcrg_allreduce_accumulators.argtypes = [C.c_int, P(vp), vp, vp]
+        l.mcrg_comm_destroy_all.argtypes = [C.c_int, P(vp)]
         _lib = l
     return _lib
 
@@ -110,6 +113,28 @@ def packed_words(L, count):
 def host_pack(spins_ptr, L, count, packed_ptr, n_threads=1):
     """int32 column-major host configurations -> 1 bit/spin transport words, on the host (mcrg_host_pack_i32_colmajor)."""
     _check(lib().mcrg_host_pack_i32_colmajor(C.c_void_p(spins_ptr), L, count, C.c_void_p(packed_ptr), n_threads))
+
+
+def _handles(ctxs):
+    return (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+
+
+def comm_init_all(ctxs):
+    """One NCCL communicator over the contexts (one per device) of THIS process: mcrg_comm_init_all."""
+    _check(lib().mcrg_comm_init_all(len(ctxs), _handles(ctxs)))
+
+
+def allreduce_accumulators(ctxs):
+    """-> exact Python ints [n_slots]: totals over all replicas and bins of all contexts (one ncclAllReduce per device)."""
+    lay = acc_layout()
+    hi = np.zeros(lay.n_slots, np.int64)
+    lo = np.zeros(lay.n_slots, np.uint64)
+    _check(lib().mcrg_allreduce_accumulators(len(ctxs), _handles(ctxs), hi.ctypes.data, lo.ctypes.data))
+    return [int(h) * (1 << 64) + int(l) for h, l in zip(hi, lo)]
+
+
+def comm_destroy_all(ctxs):
+    _check(lib().mcrg_comm_destroy_all(len(ctxs), _handles(ctxs)))
 
 
 class Context:

@@ -9,8 +9,7 @@
 #include <tuple>
 #include <vector>
 
-#include "../../include/mcrg_b200.h"
-#include "kernels.cuh"
+#include "capi_internal.cuh"
 
 using namespace mcrg;
 
@@ -73,6 +72,8 @@ struct mcrg_ctx {
     long long *acc_hi = nullptr;
     double *acc_d = nullptr;
     uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr, *TP = nullptr;
+    void *comm = nullptr;        // ncclComm_t of mcrg_comm_init_all (comm.cu), with its device limb buffer
+    void *comm_limbs = nullptr;
     int update_mode = MCRG_UPDATE_METROPOLIS;
     int *sw_parent = nullptr;  // union-find forest of the cluster update, allocated by mcrg_set_update
     uint32_t *sw_coins = nullptr;  // cluster coin bitmap, 1 bit per site (rounded up to 128 per replica)
@@ -93,6 +94,22 @@ struct mcrg_ctx {
     int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
     std::map<GraphKey, cudaGraphExec_t> graphs;
 };
+
+int mcrg_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int mcrg_ctx_device(const mcrg_ctx *c) { return c->device; }
+cudaStream_t mcrg_ctx_stream(const mcrg_ctx *c) { return c->stream; }
+void *mcrg_ctx_comm(const mcrg_ctx *c) { return c->comm; }
+void *mcrg_ctx_limbs(const mcrg_ctx *c) { return c->comm_limbs; }
+void mcrg_ctx_set_comm(mcrg_ctx *c, void *comm, void *limbs) {
+    c->comm = comm;
+    c->comm_limbs = limbs;
+}
 
 namespace {
 
@@ -434,6 +451,10 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
 
 int mcrg_ctx_destroy(mcrg_ctx *c) {
     if (!c) return 0;
+    if (c->comm) {  // a context leaving its group: the group's other members keep their (now unusable) communicators
+        mcrg_ctx *self = c;
+        mcrg_comm_destroy_all(1, &self);
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);

@@ -72,6 +72,8 @@ struct Settings {
     int quiet;              // MCRG_QUIET: suppress banners
     int cluster;            // MCRG_UPDATE=cluster: Swendsen-Wang updates (the reference's family, ising.cpp:87-155)
                             // instead of Metropolis sweeps; sweeps_per_update then counts cluster updates
+    int devices;            // MCRG_DEVICES: GPUs of this process that calc_critical_exponent spreads its chains over
+                            // (devices 0..n-1; totals by one NCCL all-reduce, mcrg_allreduce_accumulators)
 };
 Settings &settings();
 }  // namespace mcrg_b200

@@ -82,9 +82,11 @@ static long env_long(const char *name, long dflt) {
 Settings &settings() {
     static Settings s = {(int)env_long("MCRG_REPLICAS", 1024), (int)env_long("MCRG_SWEEPS_PER_UPDATE", 1),
                          (int)env_long("MCRG_DEVICE", 0), (std::uint64_t)env_long("MCRG_SEED", 12345),
-                         (int)env_long("MCRG_QUIET", 0), 0};
+                         (int)env_long("MCRG_QUIET", 0), 0, 1};
     static bool parsed = false;
     if (!parsed) {
+        s.devices = (int)env_long("MCRG_DEVICES", 1);
+        if (s.devices < 1) s.devices = 1;
         const char *u = std::getenv("MCRG_UPDATE");
         s.cluster = (u && (std::string(u) == "cluster" || std::string(u) == "sw")) ? 1 : 0;
         parsed = true;
@@ -97,8 +99,8 @@ Settings &settings() {
 struct DeviceBatch {
     mcrg_ctx *ctx = nullptr;
     int L = 0, replicas = 0;
-    DeviceBatch(int L_, int replicas_, std::uint32_t replica_base) : L(L_), replicas(replicas_) {
-        ck(mcrg_ctx_create(settings().device, L, replicas, settings().seed, replica_base, 1, &ctx), "mcrg_ctx_create");
+    DeviceBatch(int L_, int replicas_, std::uint32_t replica_base, int device = -1) : L(L_), replicas(replicas_) {
+        ck(mcrg_ctx_create(device < 0 ? settings().device : device, L, replicas, settings().seed, replica_base, 1, &ctx), "mcrg_ctx_create");
         if (settings().cluster) ck(mcrg_set_update(ctx, MCRG_UPDATE_CLUSTER), "mcrg_set_update");
     }
     ~DeviceBatch() { mcrg_ctx_destroy(ctx); }
@@ -139,6 +141,54 @@ static Totals fetch_totals(DeviceBatch &b) {
         }
     return t;
 }
+
+// The chains of one driver call spread over MCRG_DEVICES GPUs of this process (the role of `mpirun -n P` across nodes):
+// consecutive blocks of replica ids, one context per device, all calls asynchronous so the devices work concurrently;
+// the totals come from one NCCL all-reduce (mcrg_allreduce_accumulators = the MPI_Allreduce of mcrg.cpp:101-103), the
+// per-chain sums (for the jackknife) from each device.
+struct DeviceGroup {
+    std::vector<std::unique_ptr<DeviceBatch>> parts;
+    std::vector<mcrg_ctx *> ctxs;
+    int replicas = 0;
+    DeviceGroup(int L, int R, std::uint32_t base) : replicas(R) {
+        int n_dev = settings().devices;
+        if (n_dev > R) n_dev = R;
+        int done = 0;
+        for (int d = 0; d < n_dev; ++d) {
+            const int r = (R - done) / (n_dev - d);
+            parts.emplace_back(new DeviceBatch(L, r, base + (std::uint32_t)done, n_dev > 1 ? d : -1));
+            ctxs.push_back(parts.back()->ctx);
+            done += r;
+        }
+        if (n_dev > 1) ck(mcrg_comm_init_all(n_dev, ctxs.data()), "mcrg_comm_init_all");
+    }
+    template <typename F>
+    void each(F f) {
+        for (auto &p : parts) f(*p);
+    }
+    Totals totals() {
+        Totals t;
+        for (auto &p : parts) {
+            Totals part = fetch_totals(*p);
+            if (t.v.empty()) t.v.assign(part.v.size(), 0.0L);
+            for (size_t s = 0; s < part.v.size(); ++s) t.v[s] += part.v[s];
+            for (auto &row : part.per_replica) t.per_replica.push_back(std::move(row));
+        }
+        if (parts.size() > 1) {  // the exact grand totals, reduced on the devices
+            mcrg_acc_layout lay;
+            ck(mcrg_accumulators_layout(&lay), "mcrg_accumulators_layout");
+            std::vector<std::int64_t> hi(lay.n_slots);
+            std::vector<std::uint64_t> lo(lay.n_slots);
+            ck(mcrg_allreduce_accumulators((int)ctxs.size(), ctxs.data(), hi.data(), lo.data()), "mcrg_allreduce_accumulators");
+            for (int s = 0; s < lay.n_slots; ++s) {
+                const long double x = to_ld(hi[s], lo[s]);
+                if (x != t.v[s]) throw std::runtime_error("all-reduced totals differ from the sum of the per-chain sums");
+                t.v[s] = x;
+            }
+        }
+        return t;
+    }
+};
 
 // mcrg.cpp:111-131 for the reference's operator pair (NN, NNN): A = <SbSb>-<Sb><Sb>^T, B = <SbS>-<Sb><S>^T,
 // T = A^-1 B, lambda = larger real part of T's eigenvalues
@@ -393,13 +443,15 @@ void MonteCarloRenormalizationGroup::calc_critical_exponent(int n_samples_eq, in
     const int per_replica = (n_samples + R - 1) / R;  // every chain takes ceil(n/R): SURVEY 7.0-9, no negative remainder
     const int n_lv = mcrg_levels_full(N);             // floor(log N / log b) - 1, mcrg.cpp:43
     const int spu = settings().sweeps_per_update;
-    DeviceBatch batch(N, R, mcrg_b200::take_batch_base(R));
-    ck(mcrg_set_couplings(batch.ctx, &K, 1), "mcrg_set_couplings");
-    ck(mcrg_init_hot(batch.ctx), "mcrg_init_hot");                        // Lattice(N), mcrg.cpp:49
-    ck(mcrg_sweep(batch.ctx, n_samples_eq * spu), "mcrg_sweep");            // equilibrate, mcrg.cpp:50
+    mcrg_b200::DeviceGroup group(N, R, mcrg_b200::take_batch_base(R));
+    group.each([&](DeviceBatch &b) {
+        ck(mcrg_set_couplings(b.ctx, &K, 1), "mcrg_set_couplings");
+        ck(mcrg_init_hot(b.ctx), "mcrg_init_hot");                        // Lattice(N), mcrg.cpp:49
+        ck(mcrg_sweep(b.ctx, n_samples_eq * spu), "mcrg_sweep");            // equilibrate, mcrg.cpp:50
+    });
     if (!settings().quiet) printf("Sampling %i configurations...\n", n_samples);
-    ck(mcrg_run(batch.ctx, per_replica, spu, n_lv, 0), "mcrg_run");         // the sample loop, mcrg.cpp:72-98
-    mcrg_b200::Totals tot = mcrg_b200::fetch_totals(batch);                 // the all-reduce, mcrg.cpp:101-103
+    group.each([&](DeviceBatch &b) { ck(mcrg_run(b.ctx, per_replica, spu, n_lv, 0), "mcrg_run"); });  // mcrg.cpp:72-98
+    mcrg_b200::Totals tot = group.totals();                                 // the all-reduce, mcrg.cpp:101-103
 
     lambdas_ = mcrg_b200::lambdas_from(tot.v, n_lv);
     nus_.assign(n_lv, NAN);
