@@ -213,3 +213,26 @@ def test_cluster_update_at_full_size(mc):
         ctx.sweep(2)
         b = ctx.get_spins(1, 1)[0]
     assert np.array_equal(a, b)
+
+
+def test_large_lattice_rg_flow_with_cluster_updates(mc):
+    """What the cluster update is for: at L = 1024 and K_c a Metropolis chain would need ~10^6
+    sweeps between independent samples; with cluster updates one update per sample suffices and the thermal
+    eigenvalue per blocking level comes out as in the reference's small-lattice runs: 1.95 at level 0, then
+    lambda_t = 2 (nu = 1) within a few per mille on the intermediate levels."""
+    L, n_lv, R = 1024, 6, 64
+    with mc.Context(L, R, seed=2718) as ctx:
+        ctx.set_update("cluster")
+        ctx.init_hot()
+        ctx.sweep(150)
+        ctx.run(300, 1, n_lv, 0)
+        acc, accd = ctx.accumulators()
+
+    def lambdas(v):
+        return mc.analysis.rg_eigenvalues(mc.analysis.unpack_slots(v[:-1], n_lv), ops=(0, 1))[0]
+
+    est, err = mc.analysis.jackknife(grouped(acc[:, 0, :], accd[:, 0, :], 16), lambdas)
+    print("lambda", [round(float(x), 4) for x in est], "err", [round(float(x), 4) for x in err])
+    assert abs(est[0] - 1.95) < max(0.03, 4 * err[0]), (est[0], err[0])
+    for lv in range(1, n_lv):
+        assert abs(est[lv] - 2.0) < max(0.03, 4 * err[lv]), (lv, est[lv], err[lv])
