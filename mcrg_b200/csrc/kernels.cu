@@ -498,6 +498,51 @@ __global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_l
 
 // ---- pieces shared by k_tail and k_resident ---------------------------------------------------------------------
 
+// Levels lv0..n_levels with at most 32 rows of one word each, held one row per lane in registers of warp 0: neighbours
+// by shuffle, counters by warp reduction, no block barrier until the end.  Same formulas as measure_rowN / block_pairN
+// (W == 1: a row's horizontal neighbours wrap inside its own word), same tie-coin keys.  All threads of the CTA call
+// this; ends synchronised.
+__device__ __forceinline__ void pyramid_tail_warp(const uint32_t *cur, int L, int lv0, int n_levels, unsigned int *red,
+                                                  uint32_t *levels_out, const size_t *level_off, int r, uint64_t seed,
+                                                  uint32_t replica, unsigned long long t) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int Ln = L >> lv0;
+        uint32_t row = lane < Ln ? cur[lane] : 0u;
+        for (int lv = lv0; lv <= n_levels; ++lv, Ln >>= 1) {
+            const int bits = Ln;  // nat_bits(Ln) for Ln <= 32
+            const uint32_t mask = valid_mask(bits);
+            const int below = (lane + 1 >= Ln) ? 0 : lane + 1;
+            const uint32_t r0 = row, r1 = __shfl_sync(0xFFFFFFFFu, row, below);
+            Counts c = {0u, 0u, 0u, 0u};
+            if (lane < Ln) {
+                const uint32_t r0u = shift_up_index(r0, r0, bits, mask), r1u = shift_up_index(r1, r1, bits, mask);
+                const uint32_t r1d = shift_down_index(r1, r1, bits, mask);
+                c.anti_nn = popc32(r0 ^ r0u) + popc32(r0 ^ r1);
+                c.anti_nnn = popc32(r0 ^ r1u) + popc32(r0 ^ r1d);
+                c.odd_plaq = popc32(r0 ^ r0u ^ r1 ^ r1u);
+                c.up = popc32(r0);
+            }
+            warp_reduce_to(c, red + lv * 4);
+            if (lv < n_levels) {
+                const int Lb = Ln >> 1;
+                uint32_t o = 0u;
+                if (lane < Ln && !(lane & 1)) {  // rows (lane, lane + 1) -> block row lane / 2
+                    uint32_t m, tie;
+                    majority4(r0, r0 >> 1, r1, r1 >> 1, m, tie);
+                    o = compress_even(m);
+                    tie = compress_even(tie);
+                    if (tie) o |= tie & tie_word(seed, (uint32_t)(lane >> 1), replica, t, lv + 1);
+                }
+                row = __shfl_sync(0xFFFFFFFFu, o, (2 * lane) & 31);  // block row i was computed by lane 2i
+                if (lane >= Lb) row = 0u;
+                if (levels_out && lane < Lb) levels_out[level_off[lv + 1] + (size_t)r * Lb + lane] = row;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // Levels start..n_levels of one replica, level `start` already in `cur` (natural layout): correlator popcounts of
 // every level into red[lv*4..], blocking to the next level ping-ponging between cur and nxt.  Optionally mirrors
 // every produced level to global memory.  All threads of the CTA call this; ends synchronised.
@@ -506,6 +551,10 @@ __device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, in
                                                 uint32_t replica, unsigned long long t) {
     for (int lv = start; lv <= n_levels; ++lv) {
         const int Ln = L >> lv, Wn = nat_words(Ln), lw = ilog2(Wn);
+        if (Ln <= 32) {  // one word per row and at most 32 rows: the rest of the pyramid is one warp's business
+            pyramid_tail_warp(cur, L, lv, n_levels, red, levels_out, level_off, r, seed, replica, t);
+            return;
+        }
         StripN s;
         s.x = cur;
         s.W = Wn;
