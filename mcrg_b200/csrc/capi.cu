@@ -58,6 +58,7 @@ struct mcrg_ctx {
     cudaEvent_t ev_meas[2] = {nullptr, nullptr}, ev_pyr[2] = {nullptr, nullptr};
     bool pyr_pending[2] = {false, false};
     int overlap = 1;      // run the pyramid on stream2
+    int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
     int last_parity = 0;  // which level-1 / popcount buffer the last measurement used
     size_t level1_words = 0, cnt_cells = 0;
@@ -304,14 +305,28 @@ bool use_resident(const mcrg_ctx *c) {
     return c->resident && c->strip_rows == 0 && c->L <= RESIDENT_MAX_L && c->update_mode == MCRG_UPDATE_METROPOLIS;
 }
 
+void enqueue_resident_launch(mcrg_ctx *c, bool measure, int n_samples, int m, int n_lv, int accumulate, int bin, unsigned long long t_off);
+
+// a resident run, split into launches of at most 2^22 samples (the kernel keeps 64-bit sums per launch, see k_resident)
 void enqueue_resident(mcrg_ctx *c, bool measure, int n_samples, int m, int n_lv, int accumulate, int bin) {
+    const int cap = measure ? c->resident_cap : n_samples;
+    unsigned long long t_off = 0;
+    for (int done = 0; done < n_samples;) {
+        const int n = n_samples - done < cap ? n_samples - done : cap;
+        enqueue_resident_launch(c, measure, n, m, n_lv, accumulate, bin, t_off);
+        t_off += (unsigned long long)n * m;
+        done += n;
+    }
+}
+
+void enqueue_resident_launch(mcrg_ctx *c, bool measure, int n_samples, int m, int n_lv, int accumulate, int bin, unsigned long long t_off) {
     ResidentArgs a;
     a.planes = c->planes[c->cur];
     a.T4 = c->T4;
     a.T8 = c->T8;
     a.anti = c->anti;
     a.d_t = c->d_t;
-    a.t_off = 0;
+    a.t_off = t_off;
     a.seed = c->seed;
     a.replica_base = c->replica_base;
     a.L = c->L;
@@ -401,6 +416,10 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     }
     if (const char *e = getenv("MCRG_OVERLAP")) c->overlap = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT")) c->resident = atoi(e);
+    if (const char *e = getenv("MCRG_RESIDENT_MAX_SAMPLES")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= (1 << 22)) c->resident_cap = v;
+    }
     const size_t plane_words = (size_t)n_replicas * 2 * L * c->W;
     CK(cudaMalloc(&c->planes[0], plane_words * 4));
     CK(cudaMalloc(&c->planes[1], plane_words * 4));

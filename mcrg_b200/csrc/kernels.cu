@@ -604,25 +604,30 @@ __device__ __forceinline__ void add128(unsigned long long *lo, long long *hi, __
 // mcrg.cpp:86-97 with the column-major flatten of definitions.cpp:9-19 (index b*NOP+a holds X_a * Y_b).
 __device__ __forceinline__ int acc_live_slots(int n_levels) { return 3 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels; }
 
-__device__ __forceinline__ void acc_slot_value(int k, int n_levels, const long long *S_sh, int &slot, __int128 &v) {
-    const long long M = S_sh[3];
+// Slot k contributes X[ia] * X[ib] per sample, X being S_sh extended by two pseudo-entries: X_ONE = 1 and X_ABSM = |M|.
+constexpr int X_ONE = (MAX_LEVELS + 1) * 4, X_ABSM = X_ONE + 1, X_LEN = X_ABSM + 1;
+
+__device__ __forceinline__ void acc_slot_decode(int k, int n_levels, int &slot, int &ia, int &ib) {
     if (k < 3) {
-        slot = k;  // SLOT_N, SLOT_ABSM, SLOT_M2
-        v = k == 0 ? (__int128)1 : (k == 1 ? (__int128)(M < 0 ? -M : M) : (__int128)M * M);
+        slot = k;  // SLOT_N, SLOT_ABSM, SLOT_M2;  M = S_sh[3]
+        ia = k == 0 ? X_ONE : (k == 1 ? X_ABSM : 3);
+        ib = k == 2 ? 3 : X_ONE;
         return;
     }
     k -= 3;
     if (k < NOP * (n_levels + 1)) {
         const int lv = k / NOP, op = k - lv * NOP;
         slot = SLOT_S + lv * NOP + op;
-        v = S_sh[lv * 4 + op];
+        ia = lv * 4 + op;
+        ib = X_ONE;
         return;
     }
     k -= NOP * (n_levels + 1);
     if (k < NOP * NOP * (n_levels + 1)) {
         const int lv = k / (NOP * NOP), e = k - lv * NOP * NOP, b = e / NOP, al = e - b * NOP;
         slot = SLOT_SS + lv * NOP * NOP + e;
-        v = (__int128)S_sh[lv * 4 + al] * S_sh[lv * 4 + b];
+        ia = lv * 4 + al;
+        ib = lv * 4 + b;
         return;
     }
     k -= NOP * NOP * (n_levels + 1);
@@ -630,7 +635,20 @@ __device__ __forceinline__ void acc_slot_value(int k, int n_levels, const long l
     if (!vs_prev) k -= NOP * NOP * n_levels;
     const int n1 = k / (NOP * NOP), e = k - n1 * NOP * NOP, b = e / NOP, al = e - b * NOP, n = n1 + 1;
     slot = (vs_prev ? SLOT_SBS : SLOT_SB0) + n1 * NOP * NOP + e;
-    v = (__int128)S_sh[n * 4 + al] * S_sh[(vs_prev ? n - 1 : 0) * 4 + b];
+    ia = n * 4 + al;
+    ib = (vs_prev ? n - 1 : 0) * 4 + b;
+}
+
+__device__ __forceinline__ long long acc_x(const long long *S_sh, int i) {
+    if (i == X_ONE) return 1;
+    if (i == X_ABSM) return S_sh[3] < 0 ? -S_sh[3] : S_sh[3];
+    return S_sh[i];
+}
+
+__device__ __forceinline__ void acc_slot_value(int k, int n_levels, const long long *S_sh, int &slot, __int128 &v) {
+    int ia, ib;
+    acc_slot_decode(k, n_levels, slot, ia, ib);
+    v = (__int128)acc_x(S_sh, ia) * acc_x(S_sh, ib);
 }
 
 __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
@@ -696,7 +714,7 @@ template <bool MEASURE>
 __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_resident(const ResidentArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
-    __shared__ long long S_sh[(MAX_LEVELS + 1) * 4];
+    __shared__ long long S_sh[X_LEN];  // the sums of the sample + the two pseudo-entries of acc_slot_decode
     __shared__ __align__(16) McTable tab;
     __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.x;
@@ -717,9 +735,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
     q.ent = reinterpret_cast<uint4 *>(smem + lay.queue_off);
     q.cap = lay.cap;
     uint32_t *bufA = smem + lay.bufA_off, *bufB = smem + lay.bufB_off;
-    unsigned long long *acc_lo = reinterpret_cast<unsigned long long *>(smem + lay.acc_off);
+    // Accumulators of this launch: 64-bit sums are exact here — |S| <= 4 L^2 <= 2^20, products <= 2^40, and the host
+    // layer splits runs into launches of at most 2^22 samples — and flushed into the 128-bit global sums at the end.
+    // The slot decoding (which two sums a slot multiplies) is tabulated once per launch.
+    long long *acc64 = reinterpret_cast<long long *>(smem + lay.acc_off);
     const int n_live = acc_live_slots(a.n_levels);
-    long long *acc_hi = reinterpret_cast<long long *>(acc_lo + n_live);
+    int2 *dec = reinterpret_cast<int2 *>(acc64 + n_live);  // {public slot, ia | ib << 8}
 
     uint32_t *gl = a.planes + (size_t)r * 2 * L * W;
     const bool tma = tile_stage_begin(&bar, W, 2u * (uint32_t)rows * (uint32_t)W * 4u);
@@ -731,9 +752,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
     }
     if (MEASURE)
         for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
-            acc_lo[k] = 0ull;
-            acc_hi[k] = 0ll;
+            int slot, ia, ib;
+            acc_slot_decode(k, a.n_levels, slot, ia, ib);
+            acc64[k] = 0ll;
+            dec[k] = make_int2(slot, ia | (ib << 8));
         }
+    if (threadIdx.x == 0) S_sh[X_ONE] = 1;
     const uint32_t anti = a.anti[r];
     double m4 = 0.0;
     tile_stage_wait(tma, &bar);
@@ -764,14 +788,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
                 long long S[4];
                 counts_to_S((long long)(L >> lv), red[lv * 4 + 0], red[lv * 4 + 1], red[lv * 4 + 2], red[lv * 4 + 3], S);
                 for (int k = 0; k < 4; ++k) S_sh[lv * 4 + k] = S[k];
+                if (lv == 0) S_sh[X_ABSM] = S[3] < 0 ? -S[3] : S[3];
             }
             __syncthreads();
             if (a.accumulate) {
                 for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
-                    int slot;
-                    __int128 v;
-                    acc_slot_value(k, a.n_levels, S_sh, slot, v);
-                    add128(&acc_lo[k], &acc_hi[k], v);
+                    const int e = dec[k].y;
+                    acc64[k] += S_sh[e & 255] * S_sh[e >> 8];
                 }
                 if (threadIdx.x == 0) {
                     const double m = (double)S_sh[3];
@@ -803,10 +826,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
         if (a.accumulate) {
             const size_t base = ((size_t)r * a.n_bins + a.bin) * N_SLOTS;
             for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
-                int slot;
-                __int128 v;
-                acc_slot_value(k, a.n_levels, S_sh, slot, v);  // only for the slot index
-                add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], ((__int128)acc_hi[k] << 64) | (__int128)acc_lo[k]);
+                const int slot = dec[k].x;
+                add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], (__int128)acc64[k]);
             }
             if (threadIdx.x == 0) a.acc_d[((size_t)r * a.n_bins + a.bin) * N_DSLOTS + 0] += m4;
         }

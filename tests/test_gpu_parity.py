@@ -517,3 +517,27 @@ def test_sharded_contexts_give_the_totals_of_one_context(mc):
     parts = np.concatenate([totals(0, 2), totals(2, 4)], axis=0)
     assert (whole == parts).all()
     assert [int(x) for x in whole.sum(axis=0)] == [int(x) for x in parts.sum(axis=0)]
+
+
+def test_resident_runs_longer_than_one_launch(mc, monkeypatch):
+    """k_resident keeps 64-bit sums per launch and the host layer splits runs (at 2^22 samples; lowered here through
+    MCRG_RESIDENT_MAX_SAMPLES so that the split is cheap to reach): a run across several splits equals the same run
+    issued in two calls (sweep counters and accumulators continue)."""
+    L, n = 16, 2 * 700 + 5
+    monkeypatch.setenv("MCRG_RESIDENT_MAX_SAMPLES", "700")
+    with mc.Context(L, 2, seed=8) as a:
+        a.set_couplings([KC, -0.3])
+        a.init_hot()
+        a.run(n, 2, -1, 0)
+        acc_a, _ = a.accumulators()
+        spins_a, t_a = a.get_spins(), a.sweep_counter
+    monkeypatch.delenv("MCRG_RESIDENT_MAX_SAMPLES")
+    with mc.Context(L, 2, seed=8) as b:
+        b.set_couplings([KC, -0.3])
+        b.init_hot()
+        b.run(1000, 2, -1, 0)
+        b.run(n - 1000, 2, -1, 0)
+        acc_b, _ = b.accumulators()
+        lay = mc.capi.acc_layout()
+        assert (acc_a == acc_b).all() and acc_a[0, 0, lay.slot_n] == n
+        assert np.array_equal(spins_a, b.get_spins()) and t_a == b.sweep_counter == 2 * n
