@@ -60,6 +60,7 @@ struct mcrg_ctx {
     int overlap = 1;      // run the pyramid on stream2
     int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
+    int resident_threads = 0;    // 0: one thread per column walker (kernels.cu: resident_threads); MCRG_RESIDENT_THREADS forces a block size
     int last_parity = 0;  // which level-1 / popcount buffer the last measurement used
     size_t level1_words = 0, cnt_cells = 0;
     uint32_t *planes[2] = {nullptr, nullptr};
@@ -342,7 +343,7 @@ void enqueue_resident_launch(mcrg_ctx *c, bool measure, int n_samples, int m, in
     a.acc_hi = c->acc_hi;
     a.acc_d = c->acc_d;
     a.S_out = c->S_out;
-    launch_resident(a, c->n_replicas, measure, c->stream);
+    launch_resident(a, c->n_replicas, measure, c->resident_threads, c->stream);
 }
 
 int clamp_levels(const mcrg_ctx *c, int max_levels) {
@@ -416,6 +417,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     }
     if (const char *e = getenv("MCRG_OVERLAP")) c->overlap = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT")) c->resident = atoi(e);
+    if (const char *e = getenv("MCRG_RESIDENT_THREADS")) c->resident_threads = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT_MAX_SAMPLES")) {
         const int v = atoi(e);
         if (v >= 1 && v <= (1 << 22)) c->resident_cap = v;

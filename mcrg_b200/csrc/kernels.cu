@@ -32,6 +32,10 @@
 #ifndef MCRG_LEVEL_MIN_BLOCKS
 #define MCRG_LEVEL_MIN_BLOCKS 16
 #endif
+// one-warp k_resident CTAs per SM (lattices up to 64^2): 28 -> at most 72 registers per thread
+#ifndef RESIDENT_SMALL_BLOCKS
+#define RESIDENT_SMALL_BLOCKS 28
+#endif
 
 namespace mcrg {
 
@@ -710,8 +714,14 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
 // Local row lr holds global row y = lr-1; rows 0 and L+1 are periodic halo copies, refreshed after every half-sweep
 // (2W words) instead of recomputed.  Global memory is touched at the start (load), at the end (store, accumulator
 // flush) and nowhere in between; the accumulators of the launch live in shared memory as exact 128-bit sums.
-template <bool MEASURE>
-__global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_resident(const ResidentArgs a) {
+//
+// Block size = the number of column walkers a half-sweep can keep busy (resident_threads).  Lattices up to 64^2 are one
+// warp's work (32 walkers x 2 rows): SMALL instantiates the kernel for one-warp CTAs with a register budget that lets
+// RESIDENT_SMALL_BLOCKS of them share an SM, so that 4096 replicas of 64^2 (BASELINE config 2) are ONE wave of CTAs
+// (148 x 28 = 4144) and every scheduler has 7 warps to hide the Philox dependency chains behind.
+template <bool MEASURE, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_SMALL_BLOCKS : MCRG_SWEEP_MIN_BLOCKS)
+    k_resident(const ResidentArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
     __shared__ long long S_sh[X_LEN];  // the sums of the sample + the two pseudo-entries of acc_slot_decode
@@ -805,7 +815,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_reside
         }
         for (int h = 0; h < 2 * a.m; ++h) {
             const int c = h & 1;
-            mc_half_sweep(s, c, 1, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
+            if (SMALL) mc_half_sweep_t<1>(s, c, 1, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
+            else mc_half_sweep(s, c, 1, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
             uint32_t *pc = s0_plane(s, c);  // refresh this colour's periodic halo rows
             for (int w = threadIdx.x; w < 2 * W; w += blockDim.x) {
                 if (w < W) pc[w] = pc[L * W + w];
@@ -868,8 +879,8 @@ int sweep0_max_smem() {
         cudaError_t e1 = cudaFuncSetAttribute(k_sweep0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaError_t e2 = cudaFuncSetAttribute(k_sweep0<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaError_t e3 = cudaFuncSetAttribute(k_level, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaError_t e4 = cudaFuncSetAttribute(k_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaError_t e5 = cudaFuncSetAttribute(k_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaError_t e4 = cudaFuncSetAttribute(k_resident<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaError_t e5 = cudaFuncSetAttribute(k_resident<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         g_max_smem = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess && e5 == cudaSuccess) ? dyn : 48 * 1024;
         (void)cudaGetLastError();  // a refused opt-in only lowers the limit we plan with
     }
@@ -877,12 +888,29 @@ int sweep0_max_smem() {
 }
 
 
-void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st) {
+// Threads of a resident CTA = column walkers of a half-sweep: W columns x (L rows / rows per walker), where a walker
+// takes at least two rows when a warp spans several rows (W < 32, see mc_half_sweep_t).  More threads than that would
+// idle through the sweeps and only cost registers, i.e. resident CTAs per SM.  `forced` (MCRG_RESIDENT_THREADS, read per
+// context) overrides the choice for tuning and for the block-size independence test.
+int resident_threads(int L, int forced) {
+    const int W = l0_words(L);
+    int threads = pick_threads((long long)W * ((L + 1) / 2), SWEEP_THREADS);
+    if (forced >= 32 && (forced & 31) == 0 && forced <= SWEEP_THREADS) threads = forced;
+    if (threads < W) threads = W;
+    return threads;
+}
+
+void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int forced_threads, cudaStream_t st) {
     sweep0_max_smem();
-    const int threads = sweep0_threads(a.L, a.L - 2, 2);  // (L+2) rows of W words
+    const int threads = resident_threads(a.L, forced_threads);
     const size_t smem = (size_t)resident_layout(a.L, threads, a.n_levels).total_words * sizeof(uint32_t);
-    if (measure) k_resident<true><<<n_replicas, threads, smem, st>>>(a);
-    else k_resident<false><<<n_replicas, threads, smem, st>>>(a);
+    if (threads == 32) {  // one-warp CTAs, 28 per SM
+        if (measure) k_resident<true, true><<<n_replicas, threads, smem, st>>>(a);
+        else k_resident<false, true><<<n_replicas, threads, smem, st>>>(a);
+    } else {
+        if (measure) k_resident<true, false><<<n_replicas, threads, smem, st>>>(a);
+        else k_resident<false, false><<<n_replicas, threads, smem, st>>>(a);
+    }
 }
 
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st) {

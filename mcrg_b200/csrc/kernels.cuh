@@ -130,7 +130,7 @@ struct SwArgs {
 };
 void launch_sw_update(const SwArgs &a, int n_replicas, cudaStream_t st);
 
-void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, cudaStream_t st);
+void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int forced_threads, cudaStream_t st);
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st);
 void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st);
 void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st);

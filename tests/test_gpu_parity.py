@@ -541,3 +541,24 @@ def test_resident_runs_longer_than_one_launch(mc, monkeypatch):
         lay = mc.capi.acc_layout()
         assert (acc_a == acc_b).all() and acc_a[0, 0, lay.slot_n] == n
         assert np.array_equal(spins_a, b.get_spins()) and t_a == b.sweep_counter == 2 * n
+
+
+@pytest.mark.parametrize("L,forced", [(64, 96), (64, 256), (128, 256), (32, 64), (8, 128)])
+def test_resident_results_do_not_depend_on_the_block_size(mc, monkeypatch, L, forced):
+    """k_resident sizes its CTA by the number of column walkers (one warp at L <= 64, its own register budget); the
+    trajectory and every accumulator must equal those of a forced, larger block (MCRG_RESIDENT_THREADS, read per context)."""
+
+    def run():
+        with mc.Context(L, 3, seed=77, replica_base=5) as ctx:
+            ctx.set_couplings([KC, -0.3, 0.2])
+            ctx.init_hot()
+            ctx.sweep(3)
+            ctx.run(9, 2, -1, 0)
+            acc, accd = ctx.accumulators()
+            return acc, accd, ctx.get_spins(), ctx.measure()
+
+    a = run()
+    monkeypatch.setenv("MCRG_RESIDENT_THREADS", str(forced))
+    b = run()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
