@@ -364,6 +364,55 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
     else mc_half_sweep_t<0>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
 }
 
+// MEASURE phase of a strip whose words are full (bits == 32, L >= 64): the same counts and block words as measure_pair0
+// (tile.cuh), organised like the sweep.  A thread keeps ONE column w and visits the pair rows i0, i0 + di, ... (item
+// index = threadIdx.x + k * blockDim.x, so consecutive items of a thread are 256 output words apart and share a
+// tie-coin Philox call four at a time, see tie_group); every shared-memory address is "pointer + constant", the in-row
+// neighbours are one funnel shift each and the periodic wrap of w +- 1 is a per-thread constant offset.
+template <int WT>
+__device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R, int lw, int y0, uint32_t *lev1, uint64_t seed,
+                                                  uint32_t replica, unsigned long long t, Counts &cnt) {
+    const int W = WT > 0 ? WT : s.W;
+    const int w = threadIdx.x & (W - 1), i0 = threadIdx.x >> lw, di = blockDim.x >> lw;  // blockDim is a multiple of W
+    const int d_up = ((w + 1) & (W - 1)) - w, d_dn = ((w - 1) & (W - 1)) - w;
+    const uint32_t *pb = s.base + (H + 2 * i0) * W + w;  // black plane, first row of the pair
+    const uint32_t *pw = pb + s.rows * W;                // white plane
+    const int step = 2 * di * W;
+    uint32_t q = (uint32_t)(((y0 >> 1) + i0) << lw) + (uint32_t)w;
+    const uint32_t dq = (uint32_t)(di << lw);
+    TieCache coins;
+    coins.init();
+    uint32_t nn = 0, nnn = 0, pq = 0, up = 0;
+    for (int i = i0; i < (R >> 1); i += di, pb += step, pw += step, q += dq) {
+        const uint32_t b0 = pb[0], b1 = pb[W], b2 = pb[2 * W];
+        const uint32_t w0 = pw[0], w1 = pw[W], w2 = pw[2 * W];
+        const uint32_t b0u = __funnelshift_r(b0, pb[d_up], 1);          // black row y, index x'+1
+        const uint32_t w1u = __funnelshift_r(w1, pw[W + d_up], 1);
+        const uint32_t b2u = __funnelshift_r(b2, pb[2 * W + d_up], 1);
+        const uint32_t b1d = __funnelshift_l(pb[W + d_dn], b1, 1);      // black row y+1, index x'-1
+        const uint32_t w2d = __funnelshift_l(pw[2 * W + d_dn], w2, 1);
+        const uint32_t e00 = b0 ^ w0, e11 = w1 ^ b1;                    // shared by the bond and the plaquette words
+        const uint32_t f0 = w0 ^ b0u, f1 = b1 ^ w1u;
+        // even row y: black sites x = 2x', white sites x = 2x'+1
+        nn += __popc(e00) + __popc(f0) + __popc(b0 ^ w1) + __popc(w0 ^ b1);
+        nnn += __popc(b0 ^ b1) + __popc(b0 ^ b1d) + __popc(w0 ^ w1u) + __popc(w0 ^ w1);
+        pq += __popc(e00 ^ e11) + __popc(f0 ^ f1);
+        // odd row y+1: black sites x = 2x'+1, white sites x = 2x'
+        nn += __popc(f1) + __popc(e11) + __popc(b1 ^ w2) + __popc(w1 ^ b2);
+        nnn += __popc(b1 ^ b2u) + __popc(b1 ^ b2) + __popc(w1 ^ w2) + __popc(w1 ^ w2d);
+        pq += __popc(f1 ^ w2 ^ b2u) + __popc(e11 ^ b2 ^ w2);
+        up += __popc(b0) + __popc(w0) + __popc(b1) + __popc(w1);
+        uint32_t maj, tie;
+        majority4(b0, w0, b1, w1, maj, tie);
+        if (tie) maj |= tie & coins.get(seed, q, replica, t, 1);
+        lev1[q] = maj;
+    }
+    cnt.anti_nn += nn;
+    cnt.anti_nnn += nnn;
+    cnt.odd_plaq += pq;
+    cnt.up += up;
+}
+
 template <bool MEASURE>
 __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0(const SweepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -403,16 +452,21 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
         Counts c = {0u, 0u, 0u, 0u};
         const int npairs = (a.R >> 1) << lw;
         uint32_t *lev1 = a.level1 + (size_t)r * (L >> 1) * W;
-        TieCache coins;
-        coins.init();
-        for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
-            const int i = idx >> lw, w = idx & (W - 1);
-            uint32_t maj, tie;
-            measure_pair0(s, a.H + 2 * i, w, c, maj, tie);
-            const uint32_t q = (uint32_t)(((y0 >> 1) + i) << lw) + (uint32_t)w;
-            uint32_t out = maj;
-            if (tie) out |= tie & coins.get(a.seed, q, replica, t, 1);
-            lev1[q] = out;
+        if (a.bits == 32) {  // L >= 64
+            if (W == 64) measure_strip_b32<64>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);  // L = 4096
+            else measure_strip_b32<0>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);
+        } else {
+            TieCache coins;
+            coins.init();
+            for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
+                const int i = idx >> lw, w = idx & (W - 1);
+                uint32_t maj, tie;
+                measure_pair0(s, a.H + 2 * i, w, c, maj, tie);
+                const uint32_t q = (uint32_t)(((y0 >> 1) + i) << lw) + (uint32_t)w;
+                uint32_t out = maj;
+                if (tie) out |= tie & coins.get(a.seed, q, replica, t, 1);
+                lev1[q] = out;
+            }
         }
         warp_reduce_to(c, red);
         __syncthreads();
@@ -779,16 +833,21 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
             for (int k = threadIdx.x; k < (MAX_LEVELS + 1) * 4; k += blockDim.x) red[k] = 0;
             __syncthreads();
             Counts c = {0u, 0u, 0u, 0u};
-            const int npairs = (L >> 1) << lw;
-            TieCache coins;
-            coins.init();
-            for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
-                const int i = idx >> lw, w = idx & (W - 1);
-                uint32_t maj, tie;
-                measure_pair0(s, 1 + 2 * i, w, c, maj, tie);
-                uint32_t out = maj;
-                if (tie) out |= tie & coins.get(a.seed, (uint32_t)idx, replica, t, 1);
-                bufA[idx] = out;
+            if (a.bits == 32) {  // L >= 64; the level-1 lattice goes to shared memory (word idx = i * W + w)
+                if (SMALL) measure_strip_b32<1>(s, 1, L, lw, 0, bufA, a.seed, replica, t, c);
+                else measure_strip_b32<0>(s, 1, L, lw, 0, bufA, a.seed, replica, t, c);
+            } else {
+                const int npairs = (L >> 1) << lw;
+                TieCache coins;
+                coins.init();
+                for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
+                    const int i = idx >> lw, w = idx & (W - 1);
+                    uint32_t maj, tie;
+                    measure_pair0(s, 1 + 2 * i, w, c, maj, tie);
+                    uint32_t out = maj;
+                    if (tie) out |= tie & coins.get(a.seed, (uint32_t)idx, replica, t, 1);
+                    bufA[idx] = out;
+                }
             }
             warp_reduce_to(c, red);
             __syncthreads();

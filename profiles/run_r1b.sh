@@ -1,9 +1,10 @@
 set -x
-python profiles/configs_bench.py --only C2 2>&1 | tee gpurun_out/ab_c2_new.txt
-MCRG_RESIDENT_THREADS=96 python profiles/configs_bench.py --only C2 2>&1 | tee gpurun_out/ab_c2_old.txt
-MCRG_RESIDENT_THREADS=64 python profiles/configs_bench.py --only C2 2>&1 | tee gpurun_out/ab_c2_64.txt
-python profiles/configs_bench.py --only "L=128" 2>&1 | tee gpurun_out/ab_128_new.txt
-MCRG_RESIDENT_THREADS=256 python profiles/configs_bench.py --only "L=128" 2>&1 | tee gpurun_out/ab_128_old.txt
-timeout 900 python -m pytest tests -m gpu -x -q --durations=15 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-tail -25 gpurun_out/pytest_gpu.log
-python bench.py > gpurun_out/bench_r1b.json 2> gpurun_out/bench_r1b.err; tail -c 600 gpurun_out/bench_r1b.err; cut -c1-400 gpurun_out/bench_r1b.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_gpu.log
+python bench.py --no-cpu-baseline > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; tail -c 300 gpurun_out/bench_r1c.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_r1c.json'))
+print(d['value'], d['e2e']['value'], d['roofline']['kernel_ms'], d['roofline']['per_sample_ms'], d['other_schedules_per_gpu'])
+PY
+python profiles/configs_bench.py --json gpurun_out/configs_r1c.json
