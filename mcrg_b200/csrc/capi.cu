@@ -120,8 +120,12 @@ int choose_R(const mcrg_ctx *c, int H) {
     const int max_smem = sweep0_max_smem();
     auto fits = [&](int R) { return (long long)sweep0_smem_bytes(L, R, H) <= (long long)max_smem; };
     if (c->strip_rows >= 2 && c->strip_rows <= L && is_pow2(c->strip_rows) && fits(c->strip_rows)) return c->strip_rows;
+    // Rows per strip.  A half-sweep hands the R+2 / R rows of a strip to blockDim/W row groups in equal chunks (even ones
+    // when a warp spans several rows, W < 32): 64 rows suit W >= 32; with W = 16 (L = 1024) 66 rows over 16 groups cost
+    // 6 steps for 4.1 rows' worth of work, 130 rows cost 10 for 8.1 — taller strips waste fewer steps.
     int R = 4096 / W;
-    if (R > 64) R = 64;
+    const int cap = W <= 16 ? 128 : 64;
+    if (R > cap) R = cap;
     if (R < 16) R = 16;
     if (R > L) R = L;
     while (R > 2 && !fits(R)) R >>= 1;

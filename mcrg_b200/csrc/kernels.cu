@@ -186,6 +186,21 @@ __device__ __forceinline__ void mc_compare4(const U4 &r, const McTable *tab, int
     }
 }
 
+// Planes 0-3 when the two most significant bits of BOTH thresholds are zero (T4 < 1/4, i.e. |K| > 0.3466; T8 <= T4):
+// the threshold bit of planes 0 and 1 is 0 for every lane, so a lane survives them only if its uniform has both bits
+// clear and nobody is accepted yet — one LOP3 instead of six.  Same decisions as mc_compare4.
+__device__ __forceinline__ void mc_compare4_nz2(const U4 &r, const McTable *tab, uint32_t sel, uint32_t &eq, uint32_t &lt) {
+    eq &= ~(r.x | r.y);
+    const uint32_t rr[2] = {r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const uint2 t48 = *reinterpret_cast<const uint2 *>(tab->tm[2 + e]);
+        const uint32_t tm = (sel & t48.x) | (~sel & t48.y);
+        lt |= eq & ~rr[e] & tm;
+        eq &= ~(rr[e] ^ tm);
+    }
+}
+
 __device__ __forceinline__ U4 mc_philox(uint64_t seed, uint32_t word_id, uint32_t replica, uint32_t t_lo, uint32_t c3_base,
                                         int j) {
     return philox4x32_10(word_id, replica, t_lo, c3_base | ((uint32_t)j << 20), (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -235,7 +250,7 @@ struct McConst {
 // disjoint bits, so one LOP3 builds it from the running row counter.
 __device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g) { return (k.yw & g.yw_mask) | g.wid_c; }
 
-template <int P, bool B32>
+template <int P, bool B32, bool NZ2>
 __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     uint32_t eq = 0, sel = 0;
     if (it < g.n_act) {
@@ -263,7 +278,8 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
         const uint32_t word_id = mc_word_id(k, g);
         const U4 r0 = mc_philox(g.seed, word_id, g.replica, g.t_lo, g.c3_base, 0);
         const U4 r1 = mc_philox(g.seed, word_id, g.replica, g.t_lo, g.c3_base, 1);
-        mc_compare4(r0, g.tab, 0, sel, eq, lt);
+        if (NZ2) mc_compare4_nz2(r0, g.tab, sel, eq, lt);
+        else mc_compare4(r0, g.tab, 0, sel, eq, lt);
         mc_compare4(r1, g.tab, 4, sel, eq, lt);
         *k.pc = t2 ^ lt;
         k.u = k.n0;
@@ -286,11 +302,11 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     k.yw += (uint32_t)g.W;
 }
 
-template <int P0, bool B32>
+template <int P0, bool B32, bool NZ2>
 __device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
     for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
-        mc_row<P0, B32>(k, g, it);
-        mc_row<1 - P0, B32>(k, g, it + 1);
+        mc_row<P0, B32, NZ2>(k, g, it);
+        mc_row<1 - P0, B32, NZ2>(k, g, it + 1);
     }
 }
 
@@ -339,12 +355,19 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     k.yw = (uint32_t)((s.y_first + lr0) << lw);
     k.n_queued = 0;
     const int par0 = (s.y_first + lr0 + c) & 1;  // warp-uniform (W >= 32: one group per warp; W < 32: chunk even)
+    // leading threshold planes all zero (true for every coupling of the critical region): cheaper first compare
+    const bool nz2 = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1]) == 0u;
     if (s.bits == 32) {
-        if (par0) mc_walk<1, true>(k, g, n_steps);
-        else mc_walk<0, true>(k, g, n_steps);
+        if (nz2) {
+            if (par0) mc_walk<1, true, true>(k, g, n_steps);
+            else mc_walk<0, true, true>(k, g, n_steps);
+        } else {
+            if (par0) mc_walk<1, true, false>(k, g, n_steps);
+            else mc_walk<0, true, false>(k, g, n_steps);
+        }
     } else {
-        if (par0) mc_walk<1, false>(k, g, n_steps);
-        else mc_walk<0, false>(k, g, n_steps);
+        if (par0) mc_walk<1, false, false>(k, g, n_steps);
+        else mc_walk<0, false, false>(k, g, n_steps);
     }
     __syncwarp();
     const int total = min(k.n_queued, q.cap);
