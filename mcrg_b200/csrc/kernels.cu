@@ -206,6 +206,67 @@ __device__ __forceinline__ U4 mc_philox(uint64_t seed, uint32_t word_id, uint32_
     return philox4x32_10(word_id, replica, t_lo, c3_base | ((uint32_t)j << 20), (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
+// Pass 1 draws calls j = 0 and 1 of the same word.  Of the counter (word, replica, t_lo, c3_j) only `word` changes from
+// row to row and only c3 differs between the two calls, so part of rounds 0 and 1 is constant over a half-sweep:
+//   round 0:  M1 * t_lo  (hence the new c0 = hi ^ replica ^ k0 and the new c1 = lo)
+//   round 1:  M0 * c0    (its hi/lo halves)
+// McPhiloxHead holds these three words; mc_philox_pair then spends 2 + 2 x 17 instead of 2 x 20 multiplications per row.
+// Same function as philox4x32_10 (bitops.cuh), bit for bit.
+struct McPhiloxHead {
+    uint32_t b0;      // c1 after round 0
+    uint32_t h1, l1;  // hi / lo of M0 * (c0 after round 0)
+};
+
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1,%0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+}
+
+__device__ __forceinline__ McPhiloxHead mc_philox_head(uint64_t seed, uint32_t replica, uint32_t t_lo) {
+    uint32_t hi, lo;
+    mulwide(0xCD9E8D57u, t_lo, hi, lo);
+    McPhiloxHead h;
+    h.b0 = lo;
+    mulwide(0xD2511F53u, hi ^ replica ^ (uint32_t)seed, h.h1, h.l1);
+    return h;
+}
+
+__device__ __forceinline__ U4 mc_philox_rounds2to9(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    k0 += 2u * 0x9E3779B9u;
+    k1 += 2u * 0xBB67AE85u;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+        uint32_t h0, l0, h1, l1;
+        mulwide(0xD2511F53u, c0, h0, l0);
+        mulwide(0xCD9E8D57u, c2, h1, l1);
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    U4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// calls j = 0 and j = 1 of word `word_id` (c3 = c3_base | j << 20)
+__device__ __forceinline__ void mc_philox_pair(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t c3_base, U4 &r0,
+                                               U4 &r1) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t ph, pl;
+    mulwide(0xD2511F53u, word_id, ph, pl);            // round 0, the product that depends on the word
+    const uint32_t c2a = ph ^ c3_base ^ k1;           // c2 after round 0, call 0
+    const uint32_t c2b = c2a ^ (1u << 20);            //                   call 1 (c3 differs in bit 20 only)
+    const uint32_t c2n = h.h1 ^ pl ^ (k1 + 0xBB67AE85u);  // c2 after round 1 (both calls); c3 after round 1 = h.l1
+    uint32_t qh, ql;
+    mulwide(0xCD9E8D57u, c2a, qh, ql);                // round 1, call 0
+    r0 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
+    mulwide(0xCD9E8D57u, c2b, qh, ql);                // round 1, call 1
+    r1 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
+}
+
 struct McQueue {
     uint4 *ent;      // [warp][cap]: {tile word offset, undecided lanes, selector (A==1 lanes), -}
     int cap;         // entries per warp
@@ -241,6 +302,7 @@ struct McWalk {
 struct McConst {
     uint4 *my_q;         // this warp's queue segment: {offset, undecided lanes, selector, -}
     const McTable *tab;
+    McPhiloxHead head;   // the part of Philox rounds 0 and 1 that is constant over the half-sweep
     uint64_t seed;
     uint32_t replica, t_lo, c3_base, anti, mask, wid_c, yw_mask, lanes_below;
     int W, bits, d_up, d_dn, qcap, n_act;
@@ -276,8 +338,8 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
         }
         uint32_t lt = 0;                    // subset of the initial eq, hence disjoint from the A >= 2 lanes
         const uint32_t word_id = mc_word_id(k, g);
-        const U4 r0 = mc_philox(g.seed, word_id, g.replica, g.t_lo, g.c3_base, 0);
-        const U4 r1 = mc_philox(g.seed, word_id, g.replica, g.t_lo, g.c3_base, 1);
+        U4 r0, r1;
+        mc_philox_pair(g.head, g.seed, word_id, g.c3_base, r0, r1);
         if (NZ2) mc_compare4_nz2(r0, g.tab, sel, eq, lt);
         else mc_compare4(r0, g.tab, 0, sel, eq, lt);
         mc_compare4(r1, g.tab, 4, sel, eq, lt);
@@ -325,6 +387,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     g.replica = replica;
     g.t_lo = (uint32_t)sweep;
     g.c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
+    g.head = mc_philox_head(seed, replica, g.t_lo);
     g.anti = anti;
     g.mask = s.mask;
     g.lanes_below = (1u << lane) - 1u;
