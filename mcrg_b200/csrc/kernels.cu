@@ -186,18 +186,26 @@ __device__ __forceinline__ void mc_compare4(const U4 &r, const McTable *tab, int
     }
 }
 
-// Planes 0-3 when the two most significant bits of BOTH thresholds are zero (T4 < 1/4, i.e. |K| > 0.3466; T8 <= T4):
-// the threshold bit of planes 0 and 1 is 0 for every lane, so a lane survives them only if its uniform has both bits
-// clear and nobody is accepted yet — one LOP3 instead of six.  Same decisions as mc_compare4.
-__device__ __forceinline__ void mc_compare4_nz2(const U4 &r, const McTable *tab, uint32_t sel, uint32_t &eq, uint32_t &lt) {
+// Planes 0-3 when T4 < 1/4 (|K| > 0.3466, which includes the whole critical region) and therefore T8 <= T4^2 < 1/16:
+// the threshold bit of planes 0 and 1 is 0 for every lane and that of planes 2 and 3 is 0 for the A == 0 lanes, so
+//   planes 0, 1: a lane survives only if its uniform has both bits clear, nobody is accepted — one LOP3 for both;
+//   plane 2 / 3: T4's bit (template parameter XY = 2 * bit2 + bit3, the same for every lane) decides between
+//                "threshold bit = sel" (two LOP3) and "threshold bit = 0" (one).
+// Same decisions as mc_compare4 for such thresholds; mc_half_sweep_t checks the table before choosing this path.
+template <int XY>
+__device__ __forceinline__ void mc_compare4_nz(const U4 &r, uint32_t sel, uint32_t &eq, uint32_t &lt) {
     eq &= ~(r.x | r.y);
-    const uint32_t rr[2] = {r.z, r.w};
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const uint2 t48 = *reinterpret_cast<const uint2 *>(tab->tm[2 + e]);
-        const uint32_t tm = (sel & t48.x) | (~sel & t48.y);
-        lt |= eq & ~rr[e] & tm;
-        eq &= ~(rr[e] ^ tm);
+    if (XY & 2) {
+        lt |= eq & ~r.z & sel;
+        eq &= ~(r.z ^ sel);
+    } else {
+        eq &= ~r.z;
+    }
+    if (XY & 1) {
+        lt |= eq & ~r.w & sel;
+        eq &= ~(r.w ^ sel);
+    } else {
+        eq &= ~r.w;
     }
 }
 
@@ -312,7 +320,8 @@ struct McConst {
 // disjoint bits, so one LOP3 builds it from the running row counter.
 __device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g) { return (k.yw & g.yw_mask) | g.wid_c; }
 
-template <int P, bool B32, bool NZ2>
+// NZ < 0: any thresholds;  NZ = 0..3: thresholds with T4 < 1/4 whose planes 2 and 3 are NZ (see mc_compare4_nz)
+template <int P, bool B32, int NZ>
 __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     uint32_t eq = 0, sel = 0;
     if (it < g.n_act) {
@@ -327,12 +336,13 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
             n1 = B32 ? __funnelshift_l(nb, k.n0, 1) : shift_down_index(k.n0, nb, g.bits, g.mask);
         }
         const uint32_t a1 = t ^ k.u ^ g.anti, a2 = t ^ d ^ g.anti, a3 = t ^ k.n0 ^ g.anti, a4 = t ^ n1 ^ g.anti;
-        const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
-        // lanes with A >= 2 flip unconditionally; fold them in now so that only one word stays live
-        uint32_t t2 = t ^ (B32 ? (c12 | c34 | (x12 & x34)) : ((c12 | c34 | (x12 & x34)) & g.mask));
-        sel = (x12 ^ x34) & ~(c12 | c34);   // A == 1
-        eq = sel | ~(a1 | a2 | a3 | a4);    // A == 1 or A == 0: lanes that need a random number
+        // A = a1 + a2 + a3 + a4 per lane: full adder of three, then the fourth (8 LOP3 with the lines above)
+        const uint32_t s3 = a1 ^ a2 ^ a3, c3 = (a1 & a2) | (a3 & (a1 | a2));
+        uint32_t ge2 = c3 | (s3 & a4);      // A >= 2: these lanes flip unconditionally
+        sel = (s3 ^ a4) & ~c3;              // A == 1
+        eq = ~ge2;                          // A == 1 or A == 0: lanes that need a random number
         if (!B32) {
+            ge2 &= g.mask;
             sel &= g.mask;
             eq &= g.mask;
         }
@@ -340,10 +350,10 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
         const uint32_t word_id = mc_word_id(k, g);
         U4 r0, r1;
         mc_philox_pair(g.head, g.seed, word_id, g.c3_base, r0, r1);
-        if (NZ2) mc_compare4_nz2(r0, g.tab, sel, eq, lt);
+        if (NZ >= 0) mc_compare4_nz<NZ>(r0, sel, eq, lt);
         else mc_compare4(r0, g.tab, 0, sel, eq, lt);
         mc_compare4(r1, g.tab, 4, sel, eq, lt);
-        *k.pc = t2 ^ lt;
+        *k.pc = t ^ (ge2 | lt);
         k.u = k.n0;
         k.n0 = d;
     }
@@ -364,12 +374,18 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     k.yw += (uint32_t)g.W;
 }
 
-template <int P0, bool B32, bool NZ2>
+template <int P0, bool B32, int NZ>
 __device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
     for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
-        mc_row<P0, B32, NZ2>(k, g, it);
-        mc_row<1 - P0, B32, NZ2>(k, g, it + 1);
+        mc_row<P0, B32, NZ>(k, g, it);
+        mc_row<1 - P0, B32, NZ>(k, g, it + 1);
     }
+}
+
+template <bool B32, int NZ>
+__device__ __forceinline__ void mc_walk_par(int par0, McWalk &k, const McConst &g, int n_steps) {
+    if (par0) mc_walk<1, B32, NZ>(k, g, n_steps);
+    else mc_walk<0, B32, NZ>(k, g, n_steps);
 }
 
 template <int WT>
@@ -418,19 +434,17 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     k.yw = (uint32_t)((s.y_first + lr0) << lw);
     k.n_queued = 0;
     const int par0 = (s.y_first + lr0 + c) & 1;  // warp-uniform (W >= 32: one group per warp; W < 32: chunk even)
-    // leading threshold planes all zero (true for every coupling of the critical region): cheaper first compare
-    const bool nz2 = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1]) == 0u;
+    // thresholds below 1/4 (every coupling of the critical region): cheaper first compare, see mc_compare4_nz
+    const bool nz = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1] | tab->tm[2][1] | tab->tm[3][1]) == 0u;
+    const int xy = (tab->tm[2][0] ? 2 : 0) | (tab->tm[3][0] ? 1 : 0);
     if (s.bits == 32) {
-        if (nz2) {
-            if (par0) mc_walk<1, true, true>(k, g, n_steps);
-            else mc_walk<0, true, true>(k, g, n_steps);
-        } else {
-            if (par0) mc_walk<1, true, false>(k, g, n_steps);
-            else mc_walk<0, true, false>(k, g, n_steps);
-        }
+        if (!nz) mc_walk_par<true, -1>(par0, k, g, n_steps);
+        else if (xy == 0) mc_walk_par<true, 0>(par0, k, g, n_steps);
+        else if (xy == 1) mc_walk_par<true, 1>(par0, k, g, n_steps);
+        else if (xy == 2) mc_walk_par<true, 2>(par0, k, g, n_steps);
+        else mc_walk_par<true, 3>(par0, k, g, n_steps);
     } else {
-        if (par0) mc_walk<1, false, false>(k, g, n_steps);
-        else mc_walk<0, false, false>(k, g, n_steps);
+        mc_walk_par<false, -1>(par0, k, g, n_steps);
     }
     __syncwarp();
     const int total = min(k.n_queued, q.cap);

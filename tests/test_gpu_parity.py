@@ -240,6 +240,30 @@ def test_sweeps_match_scalar_metropolis(mc, L, strip, fuse, n_sweeps):
         assert np.array_equal(got2[r], want), (L, r)
 
 
+@pytest.mark.parametrize("L,strip", [(64, 0), (128, 0), (256, 16), (1024, 0)])
+def test_sweeps_match_scalar_metropolis_for_every_threshold_pattern(mc, L, strip):
+    """The first Philox call of a word is compared with code specialised on the leading bits of the acceptance thresholds
+    (kernels.cu: mc_compare4_nz, chosen per replica): T4 = exp(-4|K|) in [3/16, 1/4), [1/8, 3/16), [1/16, 1/8), below 1/16,
+    and the general path (T4 >= 1/4), both signs of K, edges included.  All must reproduce the scalar specification."""
+    o = _libs.oracle()
+    seed, base, t0, n_sweeps = 99, 11, 7, 3
+    edge = 0.25 * np.log(4.0)  # T4 = 1/4 exactly (up to rounding): the boundary between the general and the special path
+    Ks = np.array([-0.40, 0.36, -0.4406868, 0.50, -0.60, 0.69, -0.80, 1.5, -0.2, 0.05, edge, -np.nextafter(edge, 1.0), 0.25 * np.log(8.0),
+                   -0.25 * np.log(16.0)])
+    R = len(Ks)
+    with mc.Context(L, R, seed=seed, replica_base=base) as ctx:
+        ctx.set_tuning(strip_rows=strip)
+        ctx.set_couplings(Ks)
+        ctx.init_hot()
+        ctx.sweep_counter = t0
+        ctx.sweep(n_sweeps)
+        got = ctx.get_spins()
+    for r in range(R):
+        want = oracle_hot(L, seed, base + r)
+        o.orc_metropolis(L, want, Ks[r], seed, base + r, t0, n_sweeps)
+        assert np.array_equal(got[r], want), (L, r, Ks[r])
+
+
 def test_sweep_is_independent_of_strip_geometry_at_full_size(mc):
     """L = 4096 and 16384: the oracle is too slow for many sweeps, so use the size-independent property that the
     result cannot depend on the strip height or on how many sweeps are fused per launch (halo recomputation with
