@@ -513,6 +513,54 @@ __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R,
     cnt.up += up;
 }
 
+// Correlator popcounts of rows [0, n_rows) of a natural-layout lattice with full words (Ln >= 32) that sits in shared
+// memory at x[lr * Wn + w]: the same counts as measure_rowN (tile.cuh), organised like the sweep.  A thread keeps one
+// column w and walks down a contiguous block of rows; the row below and its two in-row shifts slide along in registers
+// (one row = 3 loads, 2 funnel shifts, 5 XORs, 6 popcounts), the periodic wrap of w +- 1 is a per-thread constant
+// offset.  The row below the last one is row n_rows (WRAP = false: a staged halo row) or row 0 (WRAP = true: the whole
+// periodic lattice is in shared memory).  Any block size; columns beyond blockDim are visited in further passes.
+template <bool WRAP>
+__device__ __forceinline__ void measure_rows_b32(const uint32_t *x, int Wn, int n_rows, Counts &cnt) {
+    const int cols = Wn < (int)blockDim.x ? Wn : (int)blockDim.x;  // both are powers of two or multiples of 32 >= Wn
+    if ((blockDim.x % cols) != 0) {  // (not reached with the block sizes used here; kept for exactness)
+        StripN s;
+        s.x = x;
+        s.W = Wn;
+        s.bits = 32;
+        s.mask = 0xFFFFFFFFu;
+        for (int idx = threadIdx.x; idx < n_rows * Wn; idx += blockDim.x) {
+            const int lr = idx / Wn;
+            measure_rowN(s, lr, (WRAP && lr + 1 == n_rows) ? 0 : lr + 1, idx - lr * Wn, cnt);
+        }
+        return;
+    }
+    const int n_grp = blockDim.x / cols, grp = threadIdx.x / cols;
+    const int chunk = (n_rows + n_grp - 1) / n_grp;
+    const int lr0 = grp * chunk, lr1 = min(n_rows, lr0 + chunk);
+    uint32_t nn = 0, nnn = 0, pq = 0, up = 0;
+    for (int w = threadIdx.x & (cols - 1); w < Wn && lr0 < lr1; w += cols) {
+        const int d_up = ((w + 1) & (Wn - 1)) - w, d_dn = ((w - 1) & (Wn - 1)) - w;
+        const uint32_t *p = x + lr0 * Wn + w;
+        uint32_t r0 = p[0], r0u = __funnelshift_r(r0, p[d_up], 1);
+        for (int lr = lr0; lr < lr1; ++lr) {
+            p = (WRAP && lr + 1 == n_rows) ? x + w : p + Wn;
+            const uint32_t r1 = p[0];
+            const uint32_t r1u = __funnelshift_r(r1, p[d_up], 1), r1d = __funnelshift_l(p[d_dn], r1, 1);
+            const uint32_t h = r0 ^ r0u;
+            nn += __popc(h) + __popc(r0 ^ r1);
+            nnn += __popc(r0 ^ r1u) + __popc(r0 ^ r1d);
+            pq += __popc(h ^ r1 ^ r1u);
+            up += __popc(r0);
+            r0 = r1;
+            r0u = r1u;
+        }
+    }
+    cnt.anti_nn += nn;
+    cnt.anti_nnn += nnn;
+    cnt.odd_plaq += pq;
+    cnt.up += up;
+}
+
 template <bool MEASURE>
 __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0(const SweepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -620,11 +668,7 @@ __global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_l
     __syncthreads();
 
     Counts c = {0u, 0u, 0u, 0u};
-    const int n = a.R << lw;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int lr = idx >> lw;
-        measure_rowN(s, lr, lr + 1, idx & (Wn - 1), c);
-    }
+    measure_rows_b32<false>(smem, Wn, a.R, c);  // Ln > TAIL_MAX_L here: full words; row R is the staged halo row
     if (a.out != nullptr) {
         const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
         uint32_t *out_r = a.out + (size_t)r * Lb * Wb;
@@ -719,11 +763,7 @@ __device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, in
         s.bits = nat_bits(Ln);
         s.mask = valid_mask(s.bits);
         Counts c = {0u, 0u, 0u, 0u};
-        const int n = Ln << lw;
-        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            const int lr = idx >> lw;
-            measure_rowN(s, lr, (lr + 1 == Ln) ? 0 : lr + 1, idx & (Wn - 1), c);
-        }
+        measure_rows_b32<true>(cur, Wn, Ln, c);  // Ln >= 64 here: full words, the whole periodic lattice is in `cur`
         warp_reduce_to(c, red + lv * 4);
         if (lv < n_levels) {
             const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);

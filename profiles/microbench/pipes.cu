@@ -60,6 +60,72 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t a0, uint32_t b0
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ h0 ^ h1 ^ h2 ^ h3;
 }
 
+// Mixes of two instruction types on independent registers: do the pipes overlap?
+//   A: 0 none, 1 = 16 LOP3, 2 = 16 IMAD (mad.lo), 3 = 8 IMAD.WIDE, 4 = 16 IADD3, 5 = 16 mul.hi.u32
+//   B: 0 none, 1 = 16 POPC, 2 = 4 POPC, 3 = 16 SHF, 4 = 16 IMAD (mad.lo), 5 = 16 PRMT
+template <int A, int B>
+__global__ void __launch_bounds__(256) kmix(uint32_t *out, uint32_t a0, uint32_t b0) {
+    uint32_t x0 = threadIdx.x + a0, x1 = x0 * 3 + 1, x2 = x0 * 5 + 2, x3 = x0 * 7 + 3;
+    uint32_t z0 = x0 ^ 0x1234567u, z1 = x1 ^ 0x89ABCDEu, z2 = x2 + 77u, z3 = x3 + 99u;
+    uint32_t y0 = b0 ^ x0, y1 = b0 + x1;
+    uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+#pragma unroll 1
+    for (int i = 0; i < ITER; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (A == 1) {
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x0) : "r"(y0), "r"(y1));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x1) : "r"(y0), "r"(y1));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x2) : "r"(y0), "r"(y1));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x3) : "r"(y0), "r"(y1));
+            }
+            if (A == 2) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x0) : "r"(y0), "r"(y1));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x1) : "r"(y0), "r"(y1));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x2) : "r"(y0), "r"(y1));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x3) : "r"(y0), "r"(y1));
+            }
+            if (A == 3 && (u & 1)) {
+                asm volatile("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %0, %2;\n\tmov.b64 {%0,%1}, p;\n\t}" : "+r"(x0), "=r"(h0) : "r"(0xD2511F53u));
+                asm volatile("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %0, %2;\n\tmov.b64 {%0,%1}, p;\n\t}" : "+r"(x1), "=r"(h1) : "r"(0xCD9E8D57u));
+                asm volatile("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %0, %2;\n\tmov.b64 {%0,%1}, p;\n\t}" : "+r"(x2), "=r"(h2) : "r"(0xD2511F53u));
+                asm volatile("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %0, %2;\n\tmov.b64 {%0,%1}, p;\n\t}" : "+r"(x3), "=r"(h3) : "r"(0xCD9E8D57u));
+            }
+            if (A == 4) {
+                asm volatile("{\n\t.reg .u32 t;\n\tadd.u32 t, %0, %1;\n\tadd.u32 %0, t, %2;\n\t}" : "+r"(x0) : "r"(y0), "r"(y1));
+                asm volatile("{\n\t.reg .u32 t;\n\tadd.u32 t, %0, %1;\n\tadd.u32 %0, t, %2;\n\t}" : "+r"(x1) : "r"(y0), "r"(y1));
+                asm volatile("{\n\t.reg .u32 t;\n\tadd.u32 t, %0, %1;\n\tadd.u32 %0, t, %2;\n\t}" : "+r"(x2) : "r"(y0), "r"(y1));
+                asm volatile("{\n\t.reg .u32 t;\n\tadd.u32 t, %0, %1;\n\tadd.u32 %0, t, %2;\n\t}" : "+r"(x3) : "r"(y0), "r"(y1));
+            }
+            if (A == 5) {
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x0) : "r"(0xD2511F53u));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x1) : "r"(0xCD9E8D57u));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x2) : "r"(0xD2511F53u));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x3) : "r"(0xCD9E8D57u));
+            }
+            if (B == 1 || (B == 2 && u == 0)) {
+                asm volatile("popc.b32 %0, %0;" : "+r"(z0)); asm volatile("popc.b32 %0, %0;" : "+r"(z1));
+                asm volatile("popc.b32 %0, %0;" : "+r"(z2)); asm volatile("popc.b32 %0, %0;" : "+r"(z3));
+            }
+            if (B == 3) {
+                asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(z0) : "r"(y0)); asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(z1) : "r"(y0));
+                asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(z2) : "r"(y0)); asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(z3) : "r"(y0));
+            }
+            if (B == 4) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(z0) : "r"(y0), "r"(y1));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(z1) : "r"(y0), "r"(y1));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(z2) : "r"(y0), "r"(y1));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(z3) : "r"(y0), "r"(y1));
+            }
+            if (B == 5) {
+                asm volatile("prmt.b32 %0, %0, %1, 0x3201;" : "+r"(z0) : "r"(y0)); asm volatile("prmt.b32 %0, %0, %1, 0x3201;" : "+r"(z1) : "r"(y0));
+                asm volatile("prmt.b32 %0, %0, %1, 0x3201;" : "+r"(z2) : "r"(y0)); asm volatile("prmt.b32 %0, %0, %1, 0x3201;" : "+r"(z3) : "r"(y0));
+            }
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ h0 ^ h1 ^ h2 ^ h3 ^ z0 ^ z1 ^ z2 ^ z3;
+}
+
 __device__ __forceinline__ void philox(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -128,6 +194,25 @@ int main() {
     rep("IMAD (mad.lo) x16", timeit([&] { k<3><<<blocks, 256>>>(out, 1, 2); }), ITER * 16.0);
     rep("POPC x16", timeit([&] { k<4><<<blocks, 256>>>(out, 1, 2); }), ITER * 16.0);
     rep("SHF x16", timeit([&] { k<5><<<blocks, 256>>>(out, 1, 2); }), ITER * 16.0);
+    // mixes: does the second type ride along for free (separate pipe) or add its own time (same pipe)?
+    auto mix = [&](const char *name, float ms) { printf("%-44s %8.3f ms\n", name, ms); };
+    mix("mix: 16 LOP3 alone", timeit([&] { kmix<1, 0><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 POPC alone", timeit([&] { kmix<0, 1><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 LOP3 + 16 POPC", timeit([&] { kmix<1, 1><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 LOP3 + 4 POPC", timeit([&] { kmix<1, 2><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 LOP3 + 16 SHF", timeit([&] { kmix<1, 3><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 LOP3 + 16 IMAD", timeit([&] { kmix<1, 4><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 LOP3 + 16 PRMT", timeit([&] { kmix<1, 5><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 PRMT alone", timeit([&] { kmix<0, 5><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 IMAD + 16 POPC", timeit([&] { kmix<2, 1><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 8 IMAD.WIDE alone", timeit([&] { kmix<3, 0><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 8 IMAD.WIDE + 16 POPC", timeit([&] { kmix<3, 1><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 8 IMAD.WIDE + 16 IMAD", timeit([&] { kmix<3, 4><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 8 IMAD.WIDE + 16 SHF", timeit([&] { kmix<3, 3><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 IADD3 (2 adds) alone", timeit([&] { kmix<4, 0><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 IADD3 + 16 POPC", timeit([&] { kmix<4, 1><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 mul.hi.u32 alone", timeit([&] { kmix<5, 0><<<blocks, 256>>>(out, 1, 2); }));
+    mix("mix: 16 mul.hi.u32 + 16 IMAD", timeit([&] { kmix<5, 4><<<blocks, 256>>>(out, 1, 2); }));
     const double calls = (double)blocks * 256 * (ITER / 16);
     auto repp = [&](const char *name, float ms) {
         printf("%-34s %8.3f ms  %7.2f T Philox calls/s  = %6.1f clk/SM per warp-call at 1.92 GHz  (%.2f T bit-planes of 32 lanes/s)\n", name, ms,

@@ -1,10 +1,10 @@
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/pytest_gpu.log
-python bench.py --no-cpu-baseline > gpurun_out/bench_r1f.json 2> gpurun_out/bench_r1f.err; tail -c 300 gpurun_out/bench_r1f.err
+python bench.py --no-cpu-baseline > gpurun_out/bench_r1g.json 2> gpurun_out/bench_r1g.err; tail -c 300 gpurun_out/bench_r1g.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_r1f.json'))
+d=json.load(open('gpurun_out/bench_r1g.json'))
 print(d['value'], d['e2e']['value'], d['roofline']['kernel_ms'], d['roofline']['per_sample_ms'], d['other_schedules_per_gpu'])
 PY
-python profiles/configs_bench.py --json gpurun_out/configs_r1f.json
+python profiles/configs_bench.py --json gpurun_out/configs_r1g.json
