@@ -380,8 +380,9 @@ def run_ours(args, rank, world, local_rank):
                      "kernel_ms": dom_ms, "kernel_share_of_sample": dom_ms / sample_ms if sample_ms > 0 else None,
                      "per_sample_ms": prof,
                      "compute_bound": {"what": "Philox4x32-10 + 4-plane lazy compare alone, measured live on this GPU by "
-                                               "mcrg_probe_philox_rate (see also profiles/microbench_pipes_r1.txt); a sweep needs ~2.1 "
-                                               "calls per 32 sites, so ceiling = calls/s * 32 / 2.1",
+                                               "mcrg_probe_philox_rate (see also profiles/microbench_pipes_r1.txt); a sweep draws 2 calls "
+                                               "per 32 sites in pass 1 and ~0.13 in pass 2, so ceiling = calls/s * 32 / 2.1 (the kernel "
+                                               "shares the word-independent products of rounds 0-1 between calls, which the probe does not)",
                                        "philox_T_calls_per_s": philox_calls_per_s / 1e12,
                                        "ceiling_G_sites_per_s": philox_calls_per_s / 1e9 * 32 / 2.1,
                                        "achieved_G_sites_per_s": n_loc * L * L / (dom_ms * 1e-3) / 1e9,

@@ -7,4 +7,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_sweep0 -s 40 -
 ncu -i gpurun_out/prof_sweep_r1_final.ncu-rep --page raw --csv > gpurun_out/raw_r1_final.csv
 ncu -i gpurun_out/prof_sweep_r1_final.ncu-rep --page source --csv --print-source sass > gpurun_out/sass_r1_final.csv 2>&1
 python profiles/configs_bench.py --json gpurun_out/configs_r1_final.json > gpurun_out/configs_r1_final.txt 2>&1
+python profiles/cluster_bench.py > gpurun_out/cluster_bench_r1_final.txt 2>&1
 tail -c 1500 gpurun_out/bench_r1_final.json; cat gpurun_out/bench_ref_r1_final.json | cut -c1-300
