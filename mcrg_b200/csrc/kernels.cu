@@ -711,6 +711,22 @@ __device__ __forceinline__ void pyramid_tail_warp(const uint32_t *cur, int L, in
         const int lane = threadIdx.x;
         int Ln = L >> lv0;
         uint32_t row = lane < Ln ? cur[lane] : 0u;
+        // Tie coins of ALL blocking steps of the tail in one Philox call per lane: step lv -> lv+1 has (L >> lv) / 2 output
+        // rows (each one word, its own call: tie_group(q) = q below 256); laid back to back they occupy at most Ln - 1 <= 31
+        // lanes.  The consumer of step lv (lane 2q) fetches the coins of row q from lane coin_base + q by shuffle.
+        uint32_t coin = 0u;
+        {
+            int base = 0, my_lv = -1, my_q = 0;
+            for (int lv = lv0, n = Ln >> 1; lv < n_levels; ++lv, n >>= 1) {
+                if (lane >= base && lane < base + n) {
+                    my_lv = lv + 1;
+                    my_q = lane - base;
+                }
+                base += n;
+            }
+            if (my_lv >= 0) coin = tie_word(seed, (uint32_t)my_q, replica, t, my_lv);
+        }
+        int coin_base = 0;
         for (int lv = lv0; lv <= n_levels; ++lv, Ln >>= 1) {
             const int bits = Ln;  // nat_bits(Ln) for Ln <= 32
             const uint32_t mask = valid_mask(bits);
@@ -728,13 +744,13 @@ __device__ __forceinline__ void pyramid_tail_warp(const uint32_t *cur, int L, in
             warp_reduce_to(c, red + lv * 4);
             if (lv < n_levels) {
                 const int Lb = Ln >> 1;
+                const uint32_t cw = __shfl_sync(0xFFFFFFFFu, coin, (coin_base + (lane >> 1)) & 31);
+                coin_base += Lb;
                 uint32_t o = 0u;
                 if (lane < Ln && !(lane & 1)) {  // rows (lane, lane + 1) -> block row lane / 2
                     uint32_t m, tie;
                     majority4(r0, r0 >> 1, r1, r1 >> 1, m, tie);
-                    o = compress_even(m);
-                    tie = compress_even(tie);
-                    if (tie) o |= tie & tie_word(seed, (uint32_t)(lane >> 1), replica, t, lv + 1);
+                    o = compress_even(m) | (compress_even(tie) & cw);
                 }
                 row = __shfl_sync(0xFFFFFFFFu, o, (2 * lane) & 31);  // block row i was computed by lane 2i
                 if (lane >= Lb) row = 0u;
