@@ -321,10 +321,11 @@ struct McConst {
 __device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g) { return (k.yw & g.yw_mask) | g.wid_c; }
 
 // NZ < 0: any thresholds;  NZ = 0..3: thresholds with T4 < 1/4 whose planes 2 and 3 are NZ (see mc_compare4_nz)
-template <int P, bool B32, int NZ>
+// CHK: the thread may have fewer rows than the loop runs steps (it >= n_act: step predicated off)
+template <int P, bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     uint32_t eq = 0, sel = 0;
-    if (it < g.n_act) {
+    if (!CHK || it < g.n_act) {
         const uint32_t t = *k.pc;
         const uint32_t d = k.po[g.W];
         uint32_t n1;
@@ -374,18 +375,27 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     k.yw += (uint32_t)g.W;
 }
 
-template <int P0, bool B32, int NZ>
+template <int P0, bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
     for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
-        mc_row<P0, B32, NZ>(k, g, it);
-        mc_row<1 - P0, B32, NZ>(k, g, it + 1);
+        mc_row<P0, B32, NZ, CHK>(k, g, it);
+        mc_row<1 - P0, B32, NZ, CHK>(k, g, it + 1);
     }
 }
 
-template <bool B32, int NZ>
+template <bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_walk_par(int par0, McWalk &k, const McConst &g, int n_steps) {
-    if (par0) mc_walk<1, B32, NZ>(k, g, n_steps);
-    else mc_walk<0, B32, NZ>(k, g, n_steps);
+    if (par0) mc_walk<1, B32, NZ, CHK>(k, g, n_steps);
+    else mc_walk<0, B32, NZ, CHK>(k, g, n_steps);
+}
+
+template <bool CHK>
+__device__ __forceinline__ void mc_walk_b32(bool nz, int xy, int par0, McWalk &k, const McConst &g, int n_steps) {
+    if (!nz) mc_walk_par<true, -1, CHK>(par0, k, g, n_steps);
+    else if (xy == 0) mc_walk_par<true, 0, CHK>(par0, k, g, n_steps);
+    else if (xy == 1) mc_walk_par<true, 1, CHK>(par0, k, g, n_steps);
+    else if (xy == 2) mc_walk_par<true, 2, CHK>(par0, k, g, n_steps);
+    else mc_walk_par<true, 3, CHK>(par0, k, g, n_steps);
 }
 
 template <int WT>
@@ -416,15 +426,31 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     g.d_dn = ((w - 1) & (W - 1)) - w;
     g.wid_c = (uint32_t)(c * s.L * W + w);
     g.yw_mask = (uint32_t)((s.L - 1) << lw);
-    // rows per group: even when a warp spans several groups (their row parities must agree), else just the ceiling
-    int chunk = (nrows + n_grp - 1) / n_grp;
-    if (W < 32) chunk = (chunk + 1) & ~1;
-    const int n_steps = (chunk + 1) & ~1;  // identical for every thread
-    const int lr_hi = lr_lo + nrows;
-    int lr0 = lr_lo + grp * chunk, lr1 = lr0 + chunk;
-    if (lr1 > lr_hi) lr1 = lr_hi;
-    if (lr0 >= lr_hi) lr0 = lr1 = lr_lo;  // nothing to do: park on a valid row
-    g.n_act = lr1 - lr0;
+    // Rows per group.  nrows is even (strips have an even number of rows and lose two per half-sweep; a resident lattice has
+    // L rows).  W >= 32, one row group per warp: the row PAIRS are dealt out as evenly as possible, every group gets whole
+    // pairs, so a warp runs exactly its own rows with no per-row "do I still have a row" test (`whole_pairs`).  W < 32, several
+    // groups per warp: equal even chunks (the groups of a warp must start on rows of the same parity and run the same number
+    // of steps for the full-warp ballots), the last groups may run short and test every step.
+    const bool whole_pairs = W >= 32;
+    int lr0, n_steps;
+    if (whole_pairs) {
+        const int pairs = nrows >> 1, base = pairs / n_grp, rem = pairs - base * n_grp;
+        const int first = grp * base + (grp < rem ? grp : rem), mine = base + (grp < rem ? 1 : 0);
+        lr0 = lr_lo + 2 * first;
+        n_steps = 2 * mine;  // warp-uniform
+        g.n_act = n_steps;
+    } else {
+        int chunk = (nrows + n_grp - 1) / n_grp;
+        chunk = (chunk + 1) & ~1;
+        n_steps = chunk;  // identical for every thread
+        const int lr_hi = lr_lo + nrows;
+        int lr1;
+        lr0 = lr_lo + grp * chunk;
+        lr1 = lr0 + chunk;
+        if (lr1 > lr_hi) lr1 = lr_hi;
+        if (lr0 >= lr_hi) lr0 = lr1 = lr_lo;  // nothing to do: park on a valid row
+        g.n_act = lr1 - lr0;
+    }
     McWalk k;
     k.off = (uint32_t)(lr0 * W + w);
     k.pc = plane_c + k.off;
@@ -438,13 +464,12 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     const bool nz = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1] | tab->tm[2][1] | tab->tm[3][1]) == 0u;
     const int xy = (tab->tm[2][0] ? 2 : 0) | (tab->tm[3][0] ? 1 : 0);
     if (s.bits == 32) {
-        if (!nz) mc_walk_par<true, -1>(par0, k, g, n_steps);
-        else if (xy == 0) mc_walk_par<true, 0>(par0, k, g, n_steps);
-        else if (xy == 1) mc_walk_par<true, 1>(par0, k, g, n_steps);
-        else if (xy == 2) mc_walk_par<true, 2>(par0, k, g, n_steps);
-        else mc_walk_par<true, 3>(par0, k, g, n_steps);
+        if (WT >= 32) mc_walk_b32<false>(nz, xy, par0, k, g, n_steps);        // W is a compile-time constant >= 32
+        else if (WT > 0) mc_walk_b32<true>(nz, xy, par0, k, g, n_steps);      // ... < 32
+        else if (whole_pairs) mc_walk_b32<false>(nz, xy, par0, k, g, n_steps);
+        else mc_walk_b32<true>(nz, xy, par0, k, g, n_steps);
     } else {
-        mc_walk_par<false, -1>(par0, k, g, n_steps);
+        mc_walk_par<false, -1, true>(par0, k, g, n_steps);
     }
     __syncwarp();
     const int total = min(k.n_queued, q.cap);

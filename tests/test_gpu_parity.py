@@ -215,7 +215,7 @@ def test_tie_coins_are_fair_and_keyed(mc):
 
 @pytest.mark.parametrize("L,strip,fuse,n_sweeps", [(2, 0, 1, 5), (2, 2, 2, 4), (4, 0, 1, 3), (8, 2, 1, 4), (16, 0, 2, 5), (32, 8, 1, 3), (64, 0, 1, 4),
                                                    (64, 16, 3, 7), (128, 0, 2, 3), (256, 32, 1, 2), (512, 0, 1, 2),
-                                                   (1024, 16, 2, 2)])
+                                                   (1024, 16, 2, 2), (2048, 0, 1, 2), (2048, 4, 2, 2)])
 def test_sweeps_match_scalar_metropolis(mc, L, strip, fuse, n_sweeps):
     o = _libs.oracle()
     seed, base, t0 = 0xABCDEF0123, 3, (1 << 32) - 2  # crosses the 32-bit boundary of the sweep counter
