@@ -314,6 +314,7 @@ struct McConst {
     uint64_t seed;
     uint32_t replica, t_lo, c3_base, anti, mask, wid_c, yw_mask, lanes_below;
     int W, bits, d_up, d_dn, qcap, n_act;
+    bool w_first, w_last;  // this thread's column is the first / last word of a row
 };
 
 // word id of the Philox counter: colour*L*W + y*W + w.  wid_c = colour*L*W + w and (yw & yw_mask) = (y mod L)*W occupy
@@ -322,18 +323,20 @@ __device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g
 
 // NZ < 0: any thresholds;  NZ = 0..3: thresholds with T4 < 1/4 whose planes 2 and 3 are NZ (see mc_compare4_nz)
 // CHK: the thread may have fewer rows than the loop runs steps (it >= n_act: step predicated off)
-template <int P, bool B32, int NZ, bool CHK>
+template <int WT, int P, bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     uint32_t eq = 0, sel = 0;
     if (!CHK || it < g.n_act) {
         const uint32_t t = *k.pc;
         const uint32_t d = k.po[g.W];
         uint32_t n1;
+        // in-row neighbour word w +- 1 (periodic): with W known at compile time the two possible offsets are immediates and
+        // the choice is a predicate (the compiler otherwise recomputes the offset every row to save a register)
         if (P) {
-            const uint32_t nb = k.po[g.d_up];
+            const uint32_t nb = WT > 1 ? (g.w_last ? k.po[1 - WT] : k.po[1]) : k.po[g.d_up];
             n1 = B32 ? __funnelshift_r(k.n0, nb, 1) : shift_up_index(k.n0, nb, g.bits, g.mask);
         } else {
-            const uint32_t nb = k.po[g.d_dn];
+            const uint32_t nb = WT > 1 ? (g.w_first ? k.po[WT - 1] : k.po[-1]) : k.po[g.d_dn];
             n1 = B32 ? __funnelshift_l(nb, k.n0, 1) : shift_down_index(k.n0, nb, g.bits, g.mask);
         }
         const uint32_t a1 = t ^ k.u ^ g.anti, a2 = t ^ d ^ g.anti, a3 = t ^ k.n0 ^ g.anti, a4 = t ^ n1 ^ g.anti;
@@ -375,27 +378,27 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
     k.yw += (uint32_t)g.W;
 }
 
-template <int P0, bool B32, int NZ, bool CHK>
+template <int WT, int P0, bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
     for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
-        mc_row<P0, B32, NZ, CHK>(k, g, it);
-        mc_row<1 - P0, B32, NZ, CHK>(k, g, it + 1);
+        mc_row<WT, P0, B32, NZ, CHK>(k, g, it);
+        mc_row<WT, 1 - P0, B32, NZ, CHK>(k, g, it + 1);
     }
 }
 
-template <bool B32, int NZ, bool CHK>
+template <int WT, bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_walk_par(int par0, McWalk &k, const McConst &g, int n_steps) {
-    if (par0) mc_walk<1, B32, NZ, CHK>(k, g, n_steps);
-    else mc_walk<0, B32, NZ, CHK>(k, g, n_steps);
+    if (par0) mc_walk<WT, 1, B32, NZ, CHK>(k, g, n_steps);
+    else mc_walk<WT, 0, B32, NZ, CHK>(k, g, n_steps);
 }
 
-template <bool CHK>
+template <int WT, bool CHK>
 __device__ __forceinline__ void mc_walk_b32(bool nz, int xy, int par0, McWalk &k, const McConst &g, int n_steps) {
-    if (!nz) mc_walk_par<true, -1, CHK>(par0, k, g, n_steps);
-    else if (xy == 0) mc_walk_par<true, 0, CHK>(par0, k, g, n_steps);
-    else if (xy == 1) mc_walk_par<true, 1, CHK>(par0, k, g, n_steps);
-    else if (xy == 2) mc_walk_par<true, 2, CHK>(par0, k, g, n_steps);
-    else mc_walk_par<true, 3, CHK>(par0, k, g, n_steps);
+    if (!nz) mc_walk_par<WT, true, -1, CHK>(par0, k, g, n_steps);
+    else if (xy == 0) mc_walk_par<WT, true, 0, CHK>(par0, k, g, n_steps);
+    else if (xy == 1) mc_walk_par<WT, true, 1, CHK>(par0, k, g, n_steps);
+    else if (xy == 2) mc_walk_par<WT, true, 2, CHK>(par0, k, g, n_steps);
+    else mc_walk_par<WT, true, 3, CHK>(par0, k, g, n_steps);
 }
 
 template <int WT>
@@ -422,6 +425,8 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     g.qcap = q.cap;
     const int w = threadIdx.x & (W - 1), grp = threadIdx.x >> lw;
     const int n_grp = blockDim.x >> lw;  // blockDim is a multiple of W (launch_sweep0)
+    g.w_first = w == 0;
+    g.w_last = w == W - 1;
     g.d_up = ((w + 1) & (W - 1)) - w;
     g.d_dn = ((w - 1) & (W - 1)) - w;
     g.wid_c = (uint32_t)(c * s.L * W + w);
@@ -464,12 +469,12 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     const bool nz = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1] | tab->tm[2][1] | tab->tm[3][1]) == 0u;
     const int xy = (tab->tm[2][0] ? 2 : 0) | (tab->tm[3][0] ? 1 : 0);
     if (s.bits == 32) {
-        if (WT >= 32) mc_walk_b32<false>(nz, xy, par0, k, g, n_steps);        // W is a compile-time constant >= 32
-        else if (WT > 0) mc_walk_b32<true>(nz, xy, par0, k, g, n_steps);      // ... < 32
-        else if (whole_pairs) mc_walk_b32<false>(nz, xy, par0, k, g, n_steps);
-        else mc_walk_b32<true>(nz, xy, par0, k, g, n_steps);
+        if (WT >= 32) mc_walk_b32<WT, false>(nz, xy, par0, k, g, n_steps);        // W is a compile-time constant >= 32
+        else if (WT > 0) mc_walk_b32<WT, true>(nz, xy, par0, k, g, n_steps);      // ... < 32
+        else if (whole_pairs) mc_walk_b32<0, false>(nz, xy, par0, k, g, n_steps);
+        else mc_walk_b32<0, true>(nz, xy, par0, k, g, n_steps);
     } else {
-        mc_walk_par<false, -1, true>(par0, k, g, n_steps);
+        mc_walk_par<0, false, -1, true>(par0, k, g, n_steps);
     }
     __syncwarp();
     const int total = min(k.n_queued, q.cap);
