@@ -275,16 +275,25 @@ __device__ __forceinline__ void mc_philox_pair(const McPhiloxHead &h, uint64_t s
     r1 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
 }
 
+// call j of word `word_id` with the shared head (pass 2 and the inline overflow path)
+__device__ __forceinline__ U4 mc_philox_j(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t c3_base, int j) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t ph, pl, qh, ql;
+    mulwide(0xD2511F53u, word_id, ph, pl);
+    mulwide(0xCD9E8D57u, ph ^ (c3_base | ((uint32_t)j << 20)) ^ k1, qh, ql);
+    return mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, h.h1 ^ pl ^ (k1 + 0xBB67AE85u), h.l1, k0, k1);
+}
+
 struct McQueue {
     uint4 *ent;      // [warp][cap]: {tile word offset, undecided lanes, selector (A==1 lanes), -}
     int cap;         // entries per warp
 };
 
 // finish one word whose lanes `eq` are still undecided after planes [0, 4*j0): calls j0, j0+1, ... (rare path)
-__device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0, const McTable *tab, uint64_t seed,
-                                              uint32_t word_id, uint32_t replica, uint32_t t_lo, uint32_t c3_base) {
+__device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0, const McTable *tab, const McPhiloxHead &h,
+                                              uint64_t seed, uint32_t word_id, uint32_t c3_base) {
     uint32_t lt = 0;
-    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox(seed, word_id, replica, t_lo, c3_base, j), tab, 4 * j, sel, eq, lt);
+    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox_j(h, seed, word_id, c3_base, j), tab, 4 * j, sel, eq, lt);
     return lt;
 }
 
@@ -368,7 +377,7 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
         if (slot < g.qcap) {
             g.my_q[slot] = make_uint4(k.off, eq, sel, 0u);
         } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
-            *k.pc ^= mc_finish(eq, sel, 2, g.tab, g.seed, mc_word_id(k, g), g.replica, g.t_lo, g.c3_base);
+            *k.pc ^= mc_finish(eq, sel, 2, g.tab, g.head, g.seed, mc_word_id(k, g), g.c3_base);
         }
     }
     k.n_queued += __popc(pend);
@@ -482,7 +491,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
         const uint4 ent = g.my_q[e];
         const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
         const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
-        plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, seed, word_id, replica, g.t_lo, g.c3_base);
+        plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, g.head, seed, word_id, g.c3_base);
     }
     __syncthreads();
 }
@@ -499,7 +508,39 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
 // index = threadIdx.x + k * blockDim.x, so consecutive items of a thread are 256 output words apart and share a
 // tie-coin Philox call four at a time, see tie_group); every shared-memory address is "pointer + constant", the in-row
 // neighbours are one funnel shift each and the periodic wrap of w +- 1 is a per-thread constant offset.
+struct MeasureAcc {
+    uint32_t nn, nnn, pq, up;
+};
+
+// one row-pair word: counts into `m`, returns the majority word and the tie mask of the 32 blocks
 template <int WT>
+__device__ __forceinline__ uint32_t measure_item_b32(const uint32_t *pb, const uint32_t *pw, int Wrt, int d_up, int d_dn,
+                                                     MeasureAcc &m, uint32_t &tie) {
+    const int W = WT > 0 ? WT : Wrt;
+    const uint32_t b0 = pb[0], b1 = pb[W], b2 = pb[2 * W];
+    const uint32_t w0 = pw[0], w1 = pw[W], w2 = pw[2 * W];
+    const uint32_t b0u = __funnelshift_r(b0, pb[d_up], 1);          // black row y, index x'+1
+    const uint32_t w1u = __funnelshift_r(w1, pw[W + d_up], 1);
+    const uint32_t b2u = __funnelshift_r(b2, pb[2 * W + d_up], 1);
+    const uint32_t b1d = __funnelshift_l(pb[W + d_dn], b1, 1);      // black row y+1, index x'-1
+    const uint32_t w2d = __funnelshift_l(pw[2 * W + d_dn], w2, 1);
+    const uint32_t e00 = b0 ^ w0, e11 = w1 ^ b1;                    // shared by the bond and the plaquette words
+    const uint32_t f0 = w0 ^ b0u, f1 = b1 ^ w1u;
+    // even row y: black sites x = 2x', white sites x = 2x'+1
+    m.nn += __popc(e00) + __popc(f0) + __popc(b0 ^ w1) + __popc(w0 ^ b1);
+    m.nnn += __popc(b0 ^ b1) + __popc(b0 ^ b1d) + __popc(w0 ^ w1u) + __popc(w0 ^ w1);
+    m.pq += __popc(e00 ^ e11) + __popc(f0 ^ f1);
+    // odd row y+1: black sites x = 2x'+1, white sites x = 2x'
+    m.nn += __popc(f1) + __popc(e11) + __popc(b1 ^ w2) + __popc(w1 ^ b2);
+    m.nnn += __popc(b1 ^ b2u) + __popc(b1 ^ b2) + __popc(w1 ^ w2) + __popc(w1 ^ w2d);
+    m.pq += __popc(f1 ^ w2 ^ b2u) + __popc(e11 ^ b2 ^ w2);
+    m.up += __popc(b0) + __popc(w0) + __popc(b1) + __popc(w1);
+    uint32_t maj;
+    majority4(b0, w0, b1, w1, maj, tie);
+    return maj;
+}
+
+template <int WT, bool FAST4>
 __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R, int lw, int y0, uint32_t *lev1, uint64_t seed,
                                                   uint32_t replica, unsigned long long t, Counts &cnt) {
     const int W = WT > 0 ? WT : s.W;
@@ -510,37 +551,35 @@ __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R,
     const int step = 2 * di * W;
     uint32_t q = (uint32_t)(((y0 >> 1) + i0) << lw) + (uint32_t)w;
     const uint32_t dq = (uint32_t)(di << lw);
-    TieCache coins;
-    coins.init();
-    uint32_t nn = 0, nnn = 0, pq = 0, up = 0;
-    for (int i = i0; i < (R >> 1); i += di, pb += step, pw += step, q += dq) {
-        const uint32_t b0 = pb[0], b1 = pb[W], b2 = pb[2 * W];
-        const uint32_t w0 = pw[0], w1 = pw[W], w2 = pw[2 * W];
-        const uint32_t b0u = __funnelshift_r(b0, pb[d_up], 1);          // black row y, index x'+1
-        const uint32_t w1u = __funnelshift_r(w1, pw[W + d_up], 1);
-        const uint32_t b2u = __funnelshift_r(b2, pb[2 * W + d_up], 1);
-        const uint32_t b1d = __funnelshift_l(pb[W + d_dn], b1, 1);      // black row y+1, index x'-1
-        const uint32_t w2d = __funnelshift_l(pw[2 * W + d_dn], w2, 1);
-        const uint32_t e00 = b0 ^ w0, e11 = w1 ^ b1;                    // shared by the bond and the plaquette words
-        const uint32_t f0 = w0 ^ b0u, f1 = b1 ^ w1u;
-        // even row y: black sites x = 2x', white sites x = 2x'+1
-        nn += __popc(e00) + __popc(f0) + __popc(b0 ^ w1) + __popc(w0 ^ b1);
-        nnn += __popc(b0 ^ b1) + __popc(b0 ^ b1d) + __popc(w0 ^ w1u) + __popc(w0 ^ w1);
-        pq += __popc(e00 ^ e11) + __popc(f0 ^ f1);
-        // odd row y+1: black sites x = 2x'+1, white sites x = 2x'
-        nn += __popc(f1) + __popc(e11) + __popc(b1 ^ w2) + __popc(w1 ^ b2);
-        nnn += __popc(b1 ^ b2u) + __popc(b1 ^ b2) + __popc(w1 ^ w2) + __popc(w1 ^ w2d);
-        pq += __popc(f1 ^ w2 ^ b2u) + __popc(e11 ^ b2 ^ w2);
-        up += __popc(b0) + __popc(w0) + __popc(b1) + __popc(w1);
-        uint32_t maj, tie;
-        majority4(b0, w0, b1, w1, maj, tie);
-        if (tie) maj |= tie & coins.get(seed, q, replica, t, 1);
-        lev1[q] = maj;
+    MeasureAcc m = {0u, 0u, 0u, 0u};
+    const int half = R >> 1;
+    if (FAST4 && blockDim.x == 256 && (half & (4 * di - 1)) == 0) {
+        // Every thread has a multiple of four items, 256 output words apart, the first with bits 8-9 of q clear (q = 1024 k +
+        // threadIdx.x): exactly the four words that share one tie-coin call (tie_group), in the order x, y, z, w.
+        for (int i = i0; i < half; i += 4 * di, q += 1024u) {
+            const U4 r = philox_keyed(seed, tie_group(q), replica, t, PURPOSE_TIE, 1);
+            const uint32_t coin[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e, pb += step, pw += step) {
+                uint32_t tie;
+                const uint32_t maj = measure_item_b32<WT>(pb, pw, W, d_up, d_dn, m, tie);
+                lev1[q + 256u * e] = maj | (tie & coin[e]);
+            }
+        }
+    } else {
+        TieCache coins;
+        coins.init();
+        for (int i = i0; i < half; i += di, pb += step, pw += step, q += dq) {
+            uint32_t tie;
+            uint32_t maj = measure_item_b32<WT>(pb, pw, W, d_up, d_dn, m, tie);
+            if (tie) maj |= tie & coins.get(seed, q, replica, t, 1);
+            lev1[q] = maj;
+        }
     }
-    cnt.anti_nn += nn;
-    cnt.anti_nnn += nnn;
-    cnt.odd_plaq += pq;
-    cnt.up += up;
+    cnt.anti_nn += m.nn;
+    cnt.anti_nnn += m.nnn;
+    cnt.odd_plaq += m.pq;
+    cnt.up += m.up;
 }
 
 // Correlator popcounts of rows [0, n_rows) of a natural-layout lattice with full words (Ln >= 32) that sits in shared
@@ -631,8 +670,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
         const int npairs = (a.R >> 1) << lw;
         uint32_t *lev1 = a.level1 + (size_t)r * (L >> 1) * W;
         if (a.bits == 32) {  // L >= 64
-            if (W == 64) measure_strip_b32<64>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);  // L = 4096
-            else measure_strip_b32<0>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);
+            if (W == 64) measure_strip_b32<64, true>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);  // L = 4096
+            else measure_strip_b32<0, true>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);
         } else {
             TieCache coins;
             coins.init();
@@ -1020,8 +1059,8 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
             __syncthreads();
             Counts c = {0u, 0u, 0u, 0u};
             if (a.bits == 32) {  // L >= 64; the level-1 lattice goes to shared memory (word idx = i * W + w)
-                if (SMALL) measure_strip_b32<1>(s, 1, L, lw, 0, bufA, a.seed, replica, t, c);
-                else measure_strip_b32<0>(s, 1, L, lw, 0, bufA, a.seed, replica, t, c);
+                if (SMALL) measure_strip_b32<1, false>(s, 1, L, lw, 0, bufA, a.seed, replica, t, c);
+                else measure_strip_b32<0, false>(s, 1, L, lw, 0, bufA, a.seed, replica, t, c);
             } else {
                 const int npairs = (L >> 1) << lw;
                 TieCache coins;
