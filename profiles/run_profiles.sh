@@ -1,5 +1,6 @@
 # Run on the B200 (gpurun): the bench, the reference arm, the ncu launch list, one ncu --set full capture of the measuring
 # sweep kernel and the per-configuration rates; outputs land in gpurun_out/, `python profiles/summarize.py r1_final` condenses them.
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; tail -3 gpurun_out/pytest_gpu_final.log
 python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r1_final.json 2>> gpurun_out/bench_r1_final.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 2 --warmup 1 --samples 32 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
