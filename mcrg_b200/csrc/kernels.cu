@@ -19,7 +19,7 @@
 
 // 3 CTAs of 256 threads per SM = 80 registers per thread: the row body of mc_row keeps its constants in registers
 // (measured with per-thread staging loads: 0.274 ms per launch of the headline configuration against 0.286 ms with
-// 4 CTAs / 64 registers; 0.260 ms today with TMA staging)
+// 4 CTAs / 64 registers; 0.216 ms today, see DESIGN.md section 3.1 for what was removed since)
 #ifndef MCRG_SWEEP_MIN_BLOCKS
 #define MCRG_SWEEP_MIN_BLOCKS 3
 #endif
@@ -163,10 +163,12 @@ __device__ __forceinline__ void unstage_rows(uint32_t *dst_plane, const uint32_t
 // ---- Metropolis update of a strip, device form -----------------------------------------------------------------
 // Same decisions as update_word0()/metropolis_flip_mask() in tile.cuh (the scalar specification is the oracle's
 // orc_metropolis), organised for the SM:
-//   pass 1  every word: neighbour masks, then Philox calls j = 0 and 1 back to back (two independent chains ->
-//           ILP) and 8 lazily-compared bit planes, straight-line, no divergence.  After 8 planes a lane is still
-//           undecided with probability 2^-8, i.e. ~10 % of the words keep a few undecided lanes: those words are
-//           appended to a shared-memory queue (warp-aggregated), decided lanes are written back at once.
+//   pass 1  every word: neighbour count (full adder), then Philox calls j = 0 and 1 back to back (two independent chains ->
+//           ILP; the word-independent part of rounds 0-1 is shared, mc_philox_pair) and 8 lazily-compared bit planes,
+//           straight-line, no divergence; the first four planes by code specialised on the leading threshold bits
+//           (mc_compare4_nz).  After 8 planes a lane is still undecided with probability 2^-8, i.e. ~10 % of the words
+//           keep a few undecided lanes: those words are appended to the warp's shared-memory queue (ballot rank), decided
+//           lanes are written back at once.
 //   pass 2  the queue is consumed densely, one entry per thread, calls j = 2.. until every lane is decided.
 // The per-plane threshold masks (bit k of T4 / T8 replicated over a word) are a 64-entry table in shared memory:
 // broadcast LDS on the otherwise idle LSU pipe instead of shifts on the ALU pipe, which is the binding pipe.
@@ -207,11 +209,6 @@ __device__ __forceinline__ void mc_compare4_nz(const U4 &r, uint32_t sel, uint32
     } else {
         eq &= ~r.w;
     }
-}
-
-__device__ __forceinline__ U4 mc_philox(uint64_t seed, uint32_t word_id, uint32_t replica, uint32_t t_lo, uint32_t c3_base,
-                                        int j) {
-    return philox4x32_10(word_id, replica, t_lo, c3_base | ((uint32_t)j << 20), (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
 // Pass 1 draws calls j = 0 and 1 of the same word.  Of the counter (word, replica, t_lo, c3_j) only `word` changes from
