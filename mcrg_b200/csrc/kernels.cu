@@ -16,6 +16,7 @@
 //                      live in one CTA's shared memory; one launch per block of samples.
 // The cluster update, the RGNN kernels and the boundary/bookkeeping kernels are in cluster.cu, rgnn.cu, util_kernels.cu.
 #include "kernels.cuh"
+#include "mcfast.cuh"
 
 // 3 CTAs of 256 threads per SM = 80 registers per thread: the row body of mc_row keeps its constants in registers
 // (measured with per-thread staging loads: 0.274 ms per launch of the headline configuration against 0.286 ms with
@@ -188,99 +189,6 @@ __device__ __forceinline__ void mc_compare4(const U4 &r, const McTable *tab, int
     }
 }
 
-// Planes 0-3 when T4 < 1/4 (|K| > 0.3466, which includes the whole critical region) and therefore T8 <= T4^2 < 1/16:
-// the threshold bit of planes 0 and 1 is 0 for every lane and that of planes 2 and 3 is 0 for the A == 0 lanes, so
-//   planes 0, 1: a lane survives only if its uniform has both bits clear, nobody is accepted — one LOP3 for both;
-//   plane 2 / 3: T4's bit (template parameter XY = 2 * bit2 + bit3, the same for every lane) decides between
-//                "threshold bit = sel" (two LOP3) and "threshold bit = 0" (one).
-// Same decisions as mc_compare4 for such thresholds; mc_half_sweep_t checks the table before choosing this path.
-template <int XY>
-__device__ __forceinline__ void mc_compare4_nz(const U4 &r, uint32_t sel, uint32_t &eq, uint32_t &lt) {
-    eq &= ~(r.x | r.y);
-    if (XY & 2) {
-        lt |= eq & ~r.z & sel;
-        eq &= ~(r.z ^ sel);
-    } else {
-        eq &= ~r.z;
-    }
-    if (XY & 1) {
-        lt |= eq & ~r.w & sel;
-        eq &= ~(r.w ^ sel);
-    } else {
-        eq &= ~r.w;
-    }
-}
-
-// Pass 1 draws calls j = 0 and 1 of the same word.  Of the counter (word, replica, t_lo, c3_j) only `word` changes from
-// row to row and only c3 differs between the two calls, so part of rounds 0 and 1 is constant over a half-sweep:
-//   round 0:  M1 * t_lo  (hence the new c0 = hi ^ replica ^ k0 and the new c1 = lo)
-//   round 1:  M0 * c0    (its hi/lo halves)
-// McPhiloxHead holds these three words; mc_philox_pair then spends 2 + 2 x 17 instead of 2 x 20 multiplications per row.
-// Same function as philox4x32_10 (bitops.cuh), bit for bit.
-struct McPhiloxHead {
-    uint32_t b0;      // c1 after round 0
-    uint32_t h1, l1;  // hi / lo of M0 * (c0 after round 0)
-};
-
-__device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
-    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1,%0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
-}
-
-__device__ __forceinline__ McPhiloxHead mc_philox_head(uint64_t seed, uint32_t replica, uint32_t t_lo) {
-    uint32_t hi, lo;
-    mulwide(0xCD9E8D57u, t_lo, hi, lo);
-    McPhiloxHead h;
-    h.b0 = lo;
-    mulwide(0xD2511F53u, hi ^ replica ^ (uint32_t)seed, h.h1, h.l1);
-    return h;
-}
-
-__device__ __forceinline__ U4 mc_philox_rounds2to9(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-    k0 += 2u * 0x9E3779B9u;
-    k1 += 2u * 0xBB67AE85u;
-#pragma unroll
-    for (int r = 2; r < 10; ++r) {
-        uint32_t h0, l0, h1, l1;
-        mulwide(0xD2511F53u, c0, h0, l0);
-        mulwide(0xCD9E8D57u, c2, h1, l1);
-        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c1 = l1;
-        c3 = l0;
-        c0 = n0;
-        c2 = n2;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    U4 o;
-    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
-    return o;
-}
-
-// calls j = 0 and j = 1 of word `word_id` (c3 = c3_base | j << 20)
-__device__ __forceinline__ void mc_philox_pair(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t c3_base, U4 &r0,
-                                               U4 &r1) {
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t ph, pl;
-    mulwide(0xD2511F53u, word_id, ph, pl);            // round 0, the product that depends on the word
-    const uint32_t c2a = ph ^ c3_base ^ k1;           // c2 after round 0, call 0
-    const uint32_t c2b = c2a ^ (1u << 20);            //                   call 1 (c3 differs in bit 20 only)
-    const uint32_t c2n = h.h1 ^ pl ^ (k1 + 0xBB67AE85u);  // c2 after round 1 (both calls); c3 after round 1 = h.l1
-    uint32_t qh, ql;
-    mulwide(0xCD9E8D57u, c2a, qh, ql);                // round 1, call 0
-    r0 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
-    mulwide(0xCD9E8D57u, c2b, qh, ql);                // round 1, call 1
-    r1 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
-}
-
-// call j of word `word_id` with the shared head (pass 2 and the inline overflow path)
-__device__ __forceinline__ U4 mc_philox_j(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t c3_base, int j) {
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t ph, pl, qh, ql;
-    mulwide(0xD2511F53u, word_id, ph, pl);
-    mulwide(0xCD9E8D57u, ph ^ (c3_base | ((uint32_t)j << 20)) ^ k1, qh, ql);
-    return mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, h.h1 ^ pl ^ (k1 + 0xBB67AE85u), h.l1, k0, k1);
-}
-
 struct McQueue {
     uint4 *ent;      // [warp][cap]: {tile word offset, undecided lanes, selector (A==1 lanes), -}
     int cap;         // entries per warp
@@ -346,10 +254,8 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
             n1 = B32 ? __funnelshift_l(nb, k.n0, 1) : shift_down_index(k.n0, nb, g.bits, g.mask);
         }
         const uint32_t a1 = t ^ k.u ^ g.anti, a2 = t ^ d ^ g.anti, a3 = t ^ k.n0 ^ g.anti, a4 = t ^ n1 ^ g.anti;
-        // A = a1 + a2 + a3 + a4 per lane: full adder of three, then the fourth (8 LOP3 with the lines above)
-        const uint32_t s3 = a1 ^ a2 ^ a3, c3 = (a1 & a2) | (a3 & (a1 | a2));
-        uint32_t ge2 = c3 | (s3 & a4);      // A >= 2: these lanes flip unconditionally
-        sel = (s3 ^ a4) & ~c3;              // A == 1
+        uint32_t ge2;                       // A >= 2: these lanes flip unconditionally; sel: A == 1
+        mc_neighbour_count(a1, a2, a3, a4, ge2, sel);
         eq = ~ge2;                          // A == 1 or A == 0: lanes that need a random number
         if (!B32) {
             ge2 &= g.mask;

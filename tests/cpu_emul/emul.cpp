@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../mcrg_b200/csrc/mcfast.cuh"
 #include "../../mcrg_b200/csrc/tile.cuh"
 
 using namespace mcrg;
@@ -253,6 +254,91 @@ void emul_hot_start(int L, uint64_t seed, uint32_t replica, int32_t *spins) {
     for (size_t idx = 0; idx < (size_t)2 * L * W; ++idx)
         e.planes[0][idx] = philox_keyed(seed, (uint32_t)idx, replica, 0ull, PURPOSE_INIT, 0).x & valid_mask(e.bits);
     unpack0(e, spins);
+}
+
+// ---- fast forms of the per-word arithmetic (mcfast.cuh) against the specification (bitops.cuh) -----------------------
+// The sweep kernels do not call philox4x32_10 / metropolis_flip_mask: they share the word-independent part of Philox
+// rounds 0-1 between calls, count broken bonds with a full adder and compare the first call's planes with code
+// specialised on the leading threshold bits.  Random words, keys and thresholds of every pattern: both ways must agree
+// on every bit.  Returns the number of disagreements.
+static uint64_t splitmix(uint64_t &x) {
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static void cmp4_generic(const U4 &r, uint32_t T4, uint32_t T8, int plane0, uint32_t sel, uint32_t &eq, uint32_t &lt) {
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    for (int e = 0; e < 4; ++e) {
+        const int k = plane0 + e;
+        const uint32_t t4 = ((T4 >> (31 - k)) & 1u) ? 0xFFFFFFFFu : 0u, t8 = ((T8 >> (31 - k)) & 1u) ? 0xFFFFFFFFu : 0u;
+        const uint32_t tm = (sel & t4) | (~sel & t8);
+        lt |= eq & ~rr[e] & tm;
+        eq &= ~(rr[e] ^ tm);
+    }
+}
+
+static bool same(const U4 &a, const U4 &b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
+
+int emul_fast_paths(int n_trials, uint64_t seed0) {
+    uint64_t x = seed0;
+    int bad = 0;
+    for (int it = 0; it < n_trials; ++it) {
+        const uint64_t seed = splitmix(x), t = (it & 7) ? splitmix(x) : (splitmix(x) | 0xFFFFFFFF00000000ull);
+        const uint32_t replica = (uint32_t)splitmix(x), word = (uint32_t)splitmix(x) & 0x3FFFFFFu;
+        // (1) Philox with the shared head == Philox4x32-10, every call index
+        const uint32_t c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((t >> 32) & 0xFFFFFu);
+        const McPhiloxHead h = mc_philox_head(seed, replica, (uint32_t)t);
+        U4 r0, r1;
+        mc_philox_pair(h, seed, word, c3_base, r0, r1);
+        if (!same(r0, philox_keyed(seed, word, replica, t, PURPOSE_MC, 0))) ++bad;
+        if (!same(r1, philox_keyed(seed, word, replica, t, PURPOSE_MC, 1))) ++bad;
+        for (int j = 0; j < 8; ++j)
+            if (!same(mc_philox_j(h, seed, word, c3_base, j), philox_keyed(seed, word, replica, t, PURPOSE_MC, j))) ++bad;
+        // (2) one word update: thresholds of every leading-bit pattern (and general ones), spins near and far from order
+        McParams p;
+        p.seed = seed;
+        p.anti = (splitmix(x) & 1) ? 0xFFFFFFFFu : 0u;
+        const int pat = it % 6;  // 0..3: T4 < 1/4 with planes (2,3) = pat; 4: general; 5: tiny thresholds
+        if (pat < 4) {
+            p.T4 = ((uint32_t)pat << 28) | ((uint32_t)splitmix(x) & 0x0FFFFFFFu);
+            p.T8 = (uint32_t)splitmix(x) & 0x0FFFFFFFu;
+        } else if (pat == 4) {
+            p.T4 = (uint32_t)splitmix(x) | 0x40000000u;
+            p.T8 = (uint32_t)splitmix(x);
+        } else {
+            p.T4 = (uint32_t)splitmix(x) & 0xFFFFu;
+            p.T8 = (uint32_t)splitmix(x) & 0xFFu;
+        }
+        const uint32_t tw = (uint32_t)splitmix(x);
+        uint32_t nb[4];
+        for (int k = 0; k < 4; ++k) {  // neighbours = the word itself with a sparse, dense or random set of differences
+            const uint32_t m1 = (uint32_t)splitmix(x), m2 = (uint32_t)splitmix(x), m3 = (uint32_t)splitmix(x);
+            const int kind = (int)(splitmix(x) % 3);
+            nb[k] = (tw ^ p.anti) ^ (kind == 0 ? (m1 & m2 & m3) : kind == 1 ? (m1 | m2) : m1);
+        }
+        const uint32_t want = metropolis_flip_mask(tw, nb[0], nb[1], nb[2], nb[3], 0xFFFFFFFFu, p, word, replica, t);
+        const uint32_t a1 = tw ^ nb[0] ^ p.anti, a2 = tw ^ nb[1] ^ p.anti, a3 = tw ^ nb[2] ^ p.anti, a4 = tw ^ nb[3] ^ p.anti;
+        uint32_t ge2, sel;
+        mc_neighbour_count(a1, a2, a3, a4, ge2, sel);
+        uint32_t eq = ~ge2, lt = 0u;
+        const bool nz = (p.T4 >> 30) == 0u && (p.T8 >> 28) == 0u;
+        if (nz) {
+            switch ((p.T4 >> 28) & 3u) {
+                case 0: mc_compare4_nz<0>(r0, sel, eq, lt); break;
+                case 1: mc_compare4_nz<1>(r0, sel, eq, lt); break;
+                case 2: mc_compare4_nz<2>(r0, sel, eq, lt); break;
+                default: mc_compare4_nz<3>(r0, sel, eq, lt); break;
+            }
+        } else {
+            cmp4_generic(r0, p.T4, p.T8, 0, sel, eq, lt);
+        }
+        cmp4_generic(r1, p.T4, p.T8, 4, sel, eq, lt);
+        for (int j = 2; j < 8 && eq != 0u; ++j) cmp4_generic(mc_philox_j(h, seed, word, c3_base, j), p.T4, p.T8, 4 * j, sel, eq, lt);
+        if ((ge2 | lt) != want) ++bad;
+    }
+    return bad;
 }
 
 }  // extern "C"

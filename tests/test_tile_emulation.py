@@ -22,7 +22,7 @@ KC = -0.5 * np.log(1 + np.sqrt(2))
 @pytest.fixture(scope="module")
 def emul():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC] + [os.path.join(_libs.ROOT, "mcrg_b200", "csrc", f) for f in ("bitops.cuh", "tile.cuh")]
+    deps = [SRC] + [os.path.join(_libs.ROOT, "mcrg_b200", "csrc", f) for f in ("bitops.cuh", "tile.cuh", "mcfast.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(OUT) < os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", SRC, "-o", OUT], check=True)
     e = C.CDLL(OUT)
@@ -32,6 +32,8 @@ def emul():
                                C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _libs.i64p, C.c_void_p]
     e.emul_measure.restype = C.c_int
     e.emul_hot_start.argtypes = [C.c_int, C.c_uint64, C.c_uint32, _libs.i32p]
+    e.emul_fast_paths.argtypes = [C.c_int, C.c_uint64]
+    e.emul_fast_paths.restype = C.c_int
     return e
 
 
@@ -127,3 +129,11 @@ def test_measure_with_fused_sweep_and_level_cap(emul):
     assert n == 3
     assert np.array_equal(S, want_S)
     assert np.array_equal(got_next, want_next)
+
+
+def test_fast_paths_equal_the_specification(emul):
+    """mcrg_b200/csrc/mcfast.cuh — what the sweep kernels actually execute per word: Philox with the word-independent part of
+    rounds 0-1 shared between calls, the full-adder neighbour count, the first-call compare specialised on the leading
+    threshold bits — against philox4x32_10 / metropolis_flip_mask of bitops.cuh (which tests above tie to the oracle):
+    300 000 random words, keys, sweep counters (incl. the 32-bit boundary) and thresholds of every pattern, no disagreement."""
+    assert emul.emul_fast_paths(300000, 2026) == 0
