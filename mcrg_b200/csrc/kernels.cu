@@ -1091,7 +1091,7 @@ void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int fo
     sweep0_max_smem();
     const int threads = resident_threads(a.L, forced_threads);
     const size_t smem = (size_t)resident_layout(a.L, threads, a.n_levels).total_words * sizeof(uint32_t);
-    if (threads == 32) {  // one-warp CTAs, 28 per SM
+    if (threads == 32 && l0_words(a.L) == 1) {  // one-warp CTAs of one-word rows (L <= 64), 28 per SM
         if (measure) k_resident<true, true><<<n_replicas, threads, smem, st>>>(a);
         else k_resident<false, true><<<n_replicas, threads, smem, st>>>(a);
     } else {
