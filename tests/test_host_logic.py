@@ -131,9 +131,13 @@ def test_limb_encoding_roundtrip(mc):
     assert mc.dist.limbs_to_ints(limbs + limbs[::-1]) == [a + b for a, b in zip(vals, vals[::-1])]
 
 
+@pytest.mark.parametrize("isa", ["", "avx2", "scalar"])
 @pytest.mark.parametrize("L", [2, 4, 16, 32, 64, 256])
-def test_host_pack_matches_numpy(mc, L):
-    """mcrg_host_pack_i32_colmajor (host-side format conversion, no device): bit k of word w of row y = spin (32w+k, y)."""
+def test_host_pack_matches_numpy(mc, monkeypatch, L, isa):
+    """mcrg_host_pack_i32_colmajor (host-side format conversion, no device): bit k of word w of row y = spin (32w+k, y).
+    Every instruction-set path (widest available, AVX2, scalar; MCRG_HOSTPACK_ISA is read per call)."""
+    if isa:
+        monkeypatch.setenv("MCRG_HOSTPACK_ISA", isa)
     rng = np.random.default_rng(L)
     n = 3
     spins = np.where(rng.random((n, L, L)) < 0.5, 1, -1).astype(np.int32)
