@@ -88,6 +88,8 @@ int mcrg_get_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, int32_t *ho
  * wait for that copy and packs it into the lattices (replacing replicas [first, first+count)).  One upload in flight
  * per context; the host buffer may be reused after _commit and mcrg_sync. */
 int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *ctx, int first, int count, const int32_t *pinned_host_spins);
+/* the same pipeline for configurations packed on the host first (mcrg_host_pack_i32_colmajor): 32x fewer PCIe bytes */
+int mcrg_set_spins_packed_begin(mcrg_ctx *ctx, int first, int count, const uint32_t *pinned_host_packed);
 int mcrg_set_spins_commit(mcrg_ctx *ctx);
 /* block spins produced by the last measurement; level in 1..levels of that measurement; (L>>level)^2 ints */
 /* The same upload with the 32-fold smaller PCIe transfer: pack on the host (plain CPU code on `n_threads` threads, no
@@ -97,6 +99,9 @@ int mcrg_set_spins_commit(mcrg_ctx *ctx);
 size_t mcrg_packed_words(int L, int count);
 int mcrg_host_pack_i32_colmajor(const int32_t *host_spins, int L, int count, uint32_t *packed, int n_threads);
 int mcrg_set_spins_packed(mcrg_ctx *ctx, int first, int count, const uint32_t *packed);
+/* Measurement aid for the packing above (bench.py `e2e.host_roofline`): streams `n_ints` int32 through `n_threads` host
+ * threads with no conversion and returns their sum; the caller times it.  No device work. */
+int mcrg_host_read_probe(const int32_t *buf, size_t n_ints, int n_threads, int64_t *sum_out);
 int mcrg_get_level_spins_i32_colmajor(mcrg_ctx *ctx, int replica, int level, int32_t *host_spins);
 int mcrg_get_sweep_counter(mcrg_ctx *ctx, uint64_t *t);
 int mcrg_set_sweep_counter(mcrg_ctx *ctx, uint64_t t);

@@ -56,10 +56,12 @@ def lib():
         l.mcrg_get_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_set_spins_i32_colmajor_begin.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_set_spins_commit.argtypes = [vp]
+        l.mcrg_set_spins_packed_begin.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_packed_words.argtypes = [C.c_int, C.c_int]
         l.mcrg_packed_words.restype = C.c_size_t
         l.mcrg_host_pack_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
         l.mcrg_set_spins_packed.argtypes = [vp, C.c_int, C.c_int, vp]
+        l.mcrg_host_read_probe.argtypes = [vp, C.c_size_t, C.c_int, P(C.c_int64)]
         l.mcrg_get_level_spins_i32_colmajor.argtypes = [vp, C.c_int, C.c_int, vp]
         l.mcrg_get_sweep_counter.argtypes = [vp, P(C.c_uint64)]
         l.mcrg_set_sweep_counter.argtypes = [vp, C.c_uint64]
@@ -113,6 +115,13 @@ def packed_words(L, count):
 def host_pack(spins_ptr, L, count, packed_ptr, n_threads=1):
     """int32 column-major host configurations -> 1 bit/spin transport words, on the host (mcrg_host_pack_i32_colmajor)."""
     _check(lib().mcrg_host_pack_i32_colmajor(C.c_void_p(spins_ptr), L, count, C.c_void_p(packed_ptr), n_threads))
+
+
+def host_read_probe(ptr, n_ints, n_threads=1):
+    """Streams n_ints int32 through n_threads host threads (no conversion); returns their sum.  Time it from outside."""
+    s = C.c_int64(0)
+    _check(lib().mcrg_host_read_probe(C.c_void_p(ptr), n_ints, n_threads, C.byref(s)))
+    return s.value
 
 
 def _handles(ctxs):
@@ -213,6 +222,10 @@ class Context:
     def set_spins_begin(self, host_ptr, count, first=0):
         """Start an asynchronous upload from PINNED host memory (copy stream); pair with set_spins_commit()."""
         _check(lib().mcrg_set_spins_i32_colmajor_begin(self._h, first, count, C.c_void_p(host_ptr)))
+
+    def set_spins_packed_begin(self, packed_ptr, count, first=0):
+        """Start an asynchronous upload of host-packed configurations from PINNED memory; pair with set_spins_commit()."""
+        _check(lib().mcrg_set_spins_packed_begin(self._h, first, count, C.c_void_p(packed_ptr)))
 
     def set_spins_commit(self):
         _check(lib().mcrg_set_spins_commit(self._h))

@@ -90,7 +90,7 @@ struct mcrg_ctx {
     int32_t *upload = nullptr;
     size_t upload_ints = 0;
     int up_first = 0, up_count = 0;
-    bool up_pending = false, up_packed_recorded = false;
+    bool up_pending = false, up_packed_recorded = false, up_is_packed = false;
     int last_levels = 0;
     bool measured = false;
     int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
@@ -682,12 +682,48 @@ int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *c, int first, int count, const i
     return 0;
 }
 
+// The same for configurations already packed on the host (mcrg_host_pack_i32_colmajor): 1 bit per spin over PCIe, on the
+// copy stream, overlapping whatever the context's stream is running.
+int mcrg_set_spins_packed_begin(mcrg_ctx *c, int first, int count, const uint32_t *pinned_host_packed) {
+    if (!c || !pinned_host_packed) return fail(MCRG_ERR_ARG, "null pointer");
+    if (first < 0 || count < 1 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
+    if (c->up_pending) return fail(MCRG_ERR_STATE, "an upload is already in flight: call mcrg_set_spins_commit first");
+    CK(cudaSetDevice(c->device));
+    const size_t words = mcrg_packed_words(c->L, count);
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    }
+    if (c->upload_ints < words) {
+        CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->upload) cudaFree(c->upload);
+        c->upload = nullptr;
+        c->upload_ints = 0;
+        CK(cudaMalloc(&c->upload, words * sizeof(int32_t)));
+        c->upload_ints = words;
+        c->up_packed_recorded = false;
+    }
+    if (c->up_packed_recorded) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed, 0));
+    CK(cudaMemcpyAsync(c->upload, pinned_host_packed, words * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->up_first = first;
+    c->up_count = count;
+    c->up_pending = true;
+    c->up_is_packed = true;
+    return 0;
+}
+
 int mcrg_set_spins_commit(mcrg_ctx *c) {
     if (!c) return fail(MCRG_ERR_ARG, "null context");
     if (!c->up_pending) return fail(MCRG_ERR_STATE, "no upload in flight");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-    launch_pack0(c->upload, c->planes[c->cur] + (size_t)c->up_first * 2 * c->L * c->W, c->L, c->up_count, c->stream);
+    uint32_t *dst = c->planes[c->cur] + (size_t)c->up_first * 2 * c->L * c->W;
+    if (c->up_is_packed) launch_pack_nat(reinterpret_cast<const uint32_t *>(c->upload), dst, c->L, c->up_count, c->stream);
+    else launch_pack0(c->upload, dst, c->L, c->up_count, c->stream);
+    c->up_is_packed = false;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_packed, c->stream));
     c->up_packed_recorded = true;

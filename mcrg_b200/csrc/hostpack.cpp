@@ -107,3 +107,59 @@ extern "C" int mcrg_host_pack_i32_colmajor(const int32_t *spins, int L, int coun
     for (auto &th : pool) th.join();
     return 0;
 }
+
+// Host read-bandwidth probe (bench.py's `e2e.host_roofline`): the packing above is a streaming read of the caller's int32
+// lattices; this reads the same bytes with the same thread layout and no conversion, so that the packing rate can be quoted
+// against what these host cores can read at all.  Returns the sum of the words (so the loads cannot be elided).
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("avx2"))) int64_t read_sum_avx2(const int32_t *src, size_t n_ints) {
+    __m256i a = _mm256_setzero_si256(), b = a, c = a, d = a;
+    size_t q = 0;
+    for (; q + 32 <= n_ints; q += 32) {
+        const __m256i *p = reinterpret_cast<const __m256i *>(src + q);
+        _mm_prefetch(reinterpret_cast<const char *>(p) + 4096, _MM_HINT_T0);
+        _mm_prefetch(reinterpret_cast<const char *>(p) + 4096 + 64, _MM_HINT_T0);
+        a = _mm256_add_epi32(a, _mm256_loadu_si256(p));
+        b = _mm256_add_epi32(b, _mm256_loadu_si256(p + 1));
+        c = _mm256_add_epi32(c, _mm256_loadu_si256(p + 2));
+        d = _mm256_add_epi32(d, _mm256_loadu_si256(p + 3));
+    }
+    a = _mm256_add_epi32(_mm256_add_epi32(a, b), _mm256_add_epi32(c, d));
+    alignas(32) int32_t lanes[8];
+    _mm256_store_si256(reinterpret_cast<__m256i *>(lanes), a);
+    int64_t s = 0;
+    for (int k = 0; k < 8; ++k) s += lanes[k];
+    for (; q < n_ints; ++q) s += src[q];
+    return s;
+}
+}  // namespace
+#endif
+
+extern "C" int mcrg_host_read_probe(const int32_t *buf, size_t n_ints, int n_threads, int64_t *sum_out) {
+    if (!buf) return MCRG_ERR_ARG;
+    if (n_threads < 1) n_threads = 1;
+    std::vector<int64_t> part((size_t)n_threads, 0);
+    auto work = [&](int t, size_t q0, size_t q1) {
+#if defined(__x86_64__)
+        if (__builtin_cpu_supports("avx2")) {
+            part[t] = read_sum_avx2(buf + q0, q1 - q0);
+            return;
+        }
+#endif
+        int64_t s = 0;
+        for (size_t q = q0; q < q1; ++q) s += buf[q];
+        part[t] = s;
+    };
+    std::vector<std::thread> pool;
+    const size_t per = ((n_ints + n_threads - 1) / n_threads + 31) & ~(size_t)31;
+    for (int t = 0; t < n_threads; ++t) {
+        const size_t q0 = std::min(n_ints, (size_t)t * per), q1 = std::min(n_ints, q0 + per);
+        if (q0 < q1) pool.emplace_back(work, t, q0, q1);
+    }
+    for (auto &th : pool) th.join();
+    int64_t s = 0;
+    for (int64_t v : part) s += v;
+    if (sum_out) *sum_out = s;
+    return 0;
+}

@@ -69,6 +69,18 @@ def test_packed_and_pipelined_uploads_roundtrip(mc, L, R):
         assert np.array_equal(ctx.get_spins(0, R), spins)
         with pytest.raises(mc.capi.McrgError):
             ctx.set_spins_commit()  # nothing in flight
+        # the same pipeline with host-packed words, then an int32 upload again (the commit must pick the right unpacker)
+        pk = torch.from_numpy(packed.view(np.int32).copy()).pin_memory()
+        ctx.init_cold()
+        ctx.set_spins_packed_begin(pk.data_ptr(), R, first=1)
+        ctx.sweep(1)
+        ctx.set_spins_commit()
+        ctx.sync()
+        assert np.array_equal(ctx.get_spins(1, R), spins)
+        ctx.set_spins_begin(pinned.data_ptr(), R, first=0)
+        ctx.set_spins_commit()
+        ctx.sync()
+        assert np.array_equal(ctx.get_spins(0, R), spins)
 
 
 @pytest.mark.parametrize("L", [2, 4, 8, 32, 64, 128, 512])
@@ -366,6 +378,38 @@ def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start, update="me
     return dict(n=n_samples, absM=absM, M2=M2, M4=M4, S=S_sum, SS=SS, SbS=SbS, SbSb=SbSb, SB0=SB0, final=s, n_lv=n_lv)
 
 
+def assert_accumulators(mc, a, ad, want, tag=None):
+    """Every live accumulator slot of one (replica, bin) against cpu_run's exact integers; unused levels stay zero."""
+    lay = mc.capi.acc_layout()
+    n_lv = want["n_lv"]
+    assert a[lay.slot_n] == want["n"], tag
+    assert a[lay.slot_absm] == want["absM"] and a[lay.slot_m2] == want["M2"], tag
+    assert abs(ad[lay.dslot_m4] - want["M4"]) <= 1e-12 * max(1.0, want["M4"]), tag
+    for lv in range(n_lv + 1):
+        for op in range(3):
+            assert a[lay.slot_s + lv * 3 + op] == int(want["S"][lv * 3 + op]), (tag, lv, op)
+        for e in range(9):
+            assert a[lay.slot_ss + lv * 9 + e] == want["SS"][lv][e], (tag, lv, e)
+    for n in range(n_lv):
+        for e in range(9):
+            assert a[lay.slot_sbs + n * 9 + e] == want["SbS"][n * 9 + e], (tag, n, e)
+            assert a[lay.slot_ss + (n + 1) * 9 + e] == want["SbSb"][n * 9 + e], (tag, n, e)  # Sb_Sb == SS of level n+1
+            assert a[lay.slot_sb0 + n * 9 + e] == want["SB0"][n][e], (tag, n, e)
+    for lv in range(n_lv + 1, mc.capi.MAX_LEVELS + 1):  # slots of levels that do not exist stay zero
+        assert all(a[lay.slot_s + lv * 3 + op] == 0 for op in range(3)), tag
+
+
+def add_runs(a, b):
+    """Totals of two consecutive cpu_run segments (the second started from the first one's final configuration)."""
+    out = dict(n=a["n"] + b["n"], absM=a["absM"] + b["absM"], M2=a["M2"] + b["M2"], M4=a["M4"] + b["M4"], S=a["S"] + b["S"],
+               final=b["final"], n_lv=a["n_lv"])
+    out["SS"] = [[x + y for x, y in zip(u, v)] for u, v in zip(a["SS"], b["SS"])]
+    out["SB0"] = [[x + y for x, y in zip(u, v)] for u, v in zip(a["SB0"], b["SB0"])]
+    out["SbS"] = [x + y for x, y in zip(a["SbS"], b["SbS"])]
+    out["SbSb"] = [x + y for x, y in zip(a["SbSb"], b["SbSb"])]
+    return out
+
+
 @pytest.mark.parametrize("L,n_samples,m,max_levels,graphs", [(8, 5, 1, -1, 0), (16, 20, 2, -1, 1), (64, 37, 1, -1, 1),
                                                             (64, 6, 3, 2, 0), (128, 18, 1, -1, 1), (512, 3, 1, -1, 0),
                                                             (1024, 2, 2, 4, 0)])
@@ -395,24 +439,7 @@ def test_run_accumulators_match_oracle(mc, L, n_samples, m, max_levels, graphs):
     assert (acc[:, 0, :] == 0).all()  # bin 0 untouched
     for r in range(2):
         want = cpu_run(L, seed, base + r, Ks[r], t0, n_samples, m, max_levels, oracle_hot(L, seed, base + r))
-        n_lv = want["n_lv"]
-        a = acc[r, 1]
-        assert a[lay.slot_n] == want["n"]
-        assert a[lay.slot_absm] == want["absM"] and a[lay.slot_m2] == want["M2"]
-        assert abs(accd[r, 1, lay.dslot_m4] - want["M4"]) <= 1e-12 * max(1.0, want["M4"])
-        for lv in range(n_lv + 1):
-            for op in range(3):
-                assert a[lay.slot_s + lv * 3 + op] == int(want["S"][lv * 3 + op]), (r, lv, op)
-            for e in range(9):
-                assert a[lay.slot_ss + lv * 9 + e] == want["SS"][lv][e], (r, lv, e)
-        for n in range(n_lv):
-            for e in range(9):
-                assert a[lay.slot_sbs + n * 9 + e] == want["SbS"][n * 9 + e], (r, n, e)
-                assert a[lay.slot_ss + (n + 1) * 9 + e] == want["SbSb"][n * 9 + e], (r, n, e)  # Sb_Sb == SS of level n+1
-                assert a[lay.slot_sb0 + n * 9 + e] == want["SB0"][n][e], (r, n, e)
-        # slots of levels that do not exist stay zero
-        for lv in range(n_lv + 1, mc.capi.MAX_LEVELS + 1):
-            assert all(a[lay.slot_s + lv * 3 + op] == 0 for op in range(3))
+        assert_accumulators(mc, acc[r, 1], accd[r, 1], want, (L, r))
         assert np.array_equal(final[r], want["final"]), (L, r)
     if limbs_host is not None:
         tot = mc.dist.limbs_to_ints(limbs_host)
