@@ -62,6 +62,10 @@ int mcrg_levels_full(int L); /* floor(log L / log 2) - 1, mcrg.cpp:43 */
 /* tuning knobs: rows per strip of the sweep kernel (0 = heuristic; lattices up to 512^2 then use the resident kernel,
  * a non-zero value forces the strip kernel), sweeps fused per launch, CUDA-graph use */
 int mcrg_set_tuning(mcrg_ctx *ctx, int strip_rows, int fuse_sweeps, int use_graphs);
+/* Introspection of the strip-height choice (profiles/strip_scan.py, tests): with strip_rows = 0 returns the height the library
+ * picks for launches that fuse `fused_sweeps` sweeps, else evaluates the given height; *cost = the launch-time estimate the
+ * choice minimises (row steps of one SM; -1 if the strip does not fit in shared memory).  No device work. */
+int mcrg_strip_plan(mcrg_ctx *ctx, int fused_sweeps, int strip_rows, int *rows_out, double *cost_out);
 
 /* Which Markov-chain update mcrg_sweep / mcrg_run / mcrg_rgnn_run apply (one sweep-counter tick each):
  *   MCRG_UPDATE_METROPOLIS  one full checkerboard Metropolis sweep (default; the north-star hot path);
@@ -85,8 +89,9 @@ int mcrg_get_spins_i32_colmajor(mcrg_ctx *ctx, int first, int count, int32_t *ho
 /* Pipelined form of mcrg_set_spins_i32_colmajor for drivers that stream configurations through the device:
  * _begin starts copying `count` replicas from PINNED host memory to a device buffer on a separate copy stream and
  * returns at once — the copy overlaps whatever the context's stream is running; _commit makes the context's stream
- * wait for that copy and packs it into the lattices (replacing replicas [first, first+count)).  One upload in flight
- * per context; the host buffer may be reused after _commit and mcrg_sync. */
+ * wait for that copy and packs it into the lattices (replacing replicas [first, first+count)).  One upload of each kind
+ * (int32, host-packed) may be in flight per context — for disjoint replica ranges — and one _commit takes in both; the
+ * host buffer may be reused after _commit and mcrg_sync. */
 int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *ctx, int first, int count, const int32_t *pinned_host_spins);
 /* the same pipeline for configurations packed on the host first (mcrg_host_pack_i32_colmajor): 32x fewer PCIe bytes */
 int mcrg_set_spins_packed_begin(mcrg_ctx *ctx, int first, int count, const uint32_t *pinned_host_packed);
@@ -147,7 +152,7 @@ int mcrg_rgnn_accumulators_get(mcrg_ctx *ctx, double *out /* [replica][6] */);
 
 /* ---- accumulators (mcrg.cpp:53-70 containers), exact 128-bit integers ------------------------------------ */
 typedef struct {
-    int n_slots, n_dslots;
+    int n_slots;
     int slot_n, slot_absm, slot_m2; /* samples, sum |M|, sum M^2 */
     int slot_s;   /* + lv*MCRG_NOP + op                sum S^(lv)_op                         */
     int slot_ss;  /* + lv*9 + b*MCRG_NOP + a           sum S^(lv)_a S^(lv)_b   (Sb_Sb of level lv, mcrg.cpp:89) */
@@ -155,12 +160,14 @@ typedef struct {
                                                        of definitions.cpp:9-19 */
     int slot_sb0; /* + (n-1)*9 + b*MCRG_NOP + a        sum S^(n)_a S^(0)_b     (blocked level against level 0: the two-
                                                        lattice matching of approx_critical_point, mcrg.cpp:262-263) */
-    int dslot_m4; /* sum M^4 (double) */
+    int slot_m4;  /* + {0,1,2}: sum h*h, sum h*l, sum l*l with M^2 = h*2^20 + l (l < 2^20): the EXACT sum of M^4 is
+                     HH*2^40 + 2*HL*2^20 + LL (M^4 reaches 2^112 at L = 16384; the Binder cumulant's fourth moment rides
+                     the same int64 limb all-reduce as every other slot; ising.cpp:50-53 reduces E^2, M^2 likewise) */
 } mcrg_acc_layout;
 int mcrg_accumulators_layout(mcrg_acc_layout *out);
 int mcrg_accumulators_reset(mcrg_ctx *ctx);
-/* hi/lo: [replica][bin][n_slots]; d: [replica][bin][n_dslots]; any may be NULL */
-int mcrg_accumulators_get(mcrg_ctx *ctx, int64_t *hi, uint64_t *lo, double *d);
+/* hi/lo: [replica][bin][n_slots]; either may be NULL */
+int mcrg_accumulators_get(mcrg_ctx *ctx, int64_t *hi, uint64_t *lo);
 /* totals over this context's replicas and bins as 32-bit limbs held in int64 (4 limbs per slot, little endian,
  * top limb signed): summing such vectors over ranks with an int64 all-reduce (NCCL ncclInt64/ncclSum) is exact
  * and order independent for up to 2^31 ranks — the collective of mcrg.cpp:101-103.  The vector is written to

@@ -20,8 +20,15 @@ class McrgError(RuntimeError):
 
 
 class AccLayout(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("n_slots", "n_dslots", "slot_n", "slot_absm", "slot_m2", "slot_s", "slot_ss",
-                                       "slot_sbs", "slot_sb0", "dslot_m4")]
+    _fields_ = [(n, C.c_int) for n in ("n_slots", "slot_n", "slot_absm", "slot_m2", "slot_s", "slot_ss",
+                                       "slot_sbs", "slot_sb0", "slot_m4")]
+    M4_SPLIT_BITS = 20
+    dslot_m4 = 0  # index of sum M^4 in the float64 companion array Context.accumulators() derives from the exact slots
+
+    def m4(self, slots):
+        """Exact sum of M^4 from the three slots at slot_m4 (sum h*h, h*l, l*l with M^2 = h*2^20 + l), as a Python int."""
+        hh, hl, ll = (int(slots[self.slot_m4 + k]) for k in range(3))
+        return (hh << (2 * self.M4_SPLIT_BITS)) + (hl << (self.M4_SPLIT_BITS + 1)) + ll
 
 
 _lib = None
@@ -49,6 +56,7 @@ def lib():
         l.mcrg_levels_full.argtypes = [C.c_int]
         l.mcrg_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         l.mcrg_set_update.argtypes = [vp, C.c_int]
+        l.mcrg_strip_plan.argtypes = [vp, C.c_int, C.c_int, P(C.c_int), P(C.c_double)]
         l.mcrg_set_couplings.argtypes = [vp, vp, C.c_int]
         l.mcrg_init_hot.argtypes = [vp]
         l.mcrg_init_cold.argtypes = [vp]
@@ -78,7 +86,7 @@ def lib():
         l.mcrg_rgnn_accumulators_get.argtypes = [vp, vp]
         l.mcrg_accumulators_layout.argtypes = [P(AccLayout)]
         l.mcrg_accumulators_reset.argtypes = [vp]
-        l.mcrg_accumulators_get.argtypes = [vp, vp, vp, vp]
+        l.mcrg_accumulators_get.argtypes = [vp, vp, vp]
         l.mcrg_accumulators_total_limbs_device.argtypes = [vp, vp]
         l.mcrg_comm_init_all.argtypes = [C.c_int, P(vp)]
         l.mcrg_allreduce_accumulators.argtypes = [C.c_int, P(vp), vp, vp]
@@ -195,6 +203,12 @@ class Context:
 
     def set_tuning(self, strip_rows=0, fuse_sweeps=1, use_graphs=1):
         _check(lib().mcrg_set_tuning(self._h, strip_rows, fuse_sweeps, use_graphs))
+
+    def strip_plan(self, fused_sweeps=1, strip_rows=0):
+        """-> (rows per strip, estimated launch cost): the library's own choice for strip_rows = 0, else that height's estimate."""
+        r, c = C.c_int(0), C.c_double(0)
+        _check(lib().mcrg_strip_plan(self._h, fused_sweeps, strip_rows, C.byref(r), C.byref(c)))
+        return r.value, c.value
 
     def set_update(self, mode):
         """'metropolis' (default) or 'cluster' (Swendsen-Wang); applies to sweep(), run() and rgnn_run()."""
@@ -319,14 +333,15 @@ class Context:
         _check(lib().mcrg_accumulators_reset(self._h))
 
     def accumulators(self):
-        """-> (acc, accd): acc is an object array [replica, bin, slot] of exact Python ints, accd float64."""
+        """-> (acc, accd): acc is an object array [replica, bin, slot] of exact Python ints; accd[replica, bin, 0] is the sum of
+        M^4 as float64, derived here from its three exact slots (AccLayout.m4) for callers that want a plain number."""
         lay = acc_layout()
         shape = (self.n_replicas, self.n_bins, lay.n_slots)
         hi = np.zeros(shape, np.int64)
         lo = np.zeros(shape, np.uint64)
-        d = np.zeros((self.n_replicas, self.n_bins, lay.n_dslots), np.float64)
-        _check(lib().mcrg_accumulators_get(self._h, hi.ctypes.data, lo.ctypes.data, d.ctypes.data))
+        _check(lib().mcrg_accumulators_get(self._h, hi.ctypes.data, lo.ctypes.data))
         acc = hi.astype(object) * (1 << 64) + lo.astype(object)
+        d = np.array([[[float(lay.m4(acc[r, b]))] for b in range(self.n_bins)] for r in range(self.n_replicas)], np.float64)
         return acc, d
 
     def total_limbs_to_device(self, dev_ptr):

@@ -72,7 +72,6 @@ struct mcrg_ctx {
     long long *S_out = nullptr;
     unsigned long long *acc_lo = nullptr;
     long long *acc_hi = nullptr;
-    double *acc_d = nullptr;
     uint32_t *T4 = nullptr, *T8 = nullptr, *anti = nullptr, *TP = nullptr;
     void *comm = nullptr;        // ncclComm_t of mcrg_comm_init_all (comm.cu), with its device limb buffer
     void *comm_limbs = nullptr;
@@ -84,17 +83,24 @@ struct mcrg_ctx {
     double *rgnn_W = nullptr, *rgnn_acc = nullptr, *rgnn_u = nullptr, *rgnn_grad = nullptr;
     int32_t *stage = nullptr;
     size_t stage_ints = 0;
-    // pipelined upload (mcrg_set_spins_i32_colmajor_begin / _commit): copy stream + its own device buffer
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copy = nullptr, ev_packed = nullptr;
-    int32_t *upload = nullptr;
-    size_t upload_ints = 0;
-    int up_first = 0, up_count = 0;
-    bool up_pending = false, up_packed_recorded = false, up_is_packed = false;
+    // pipelined uploads (mcrg_set_spins_i32_colmajor_begin / mcrg_set_spins_packed_begin / _commit): two lanes — int32
+    // configurations and host-packed ones — each with its own copy stream and device buffer, so that one upload of each
+    // kind can be in flight at once (a driver whose host cores cannot pack fast enough sends part of a batch as int32
+    // through the copy engine while its threads pack the rest)
+    struct UploadLane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev_copy = nullptr, ev_consumed = nullptr;
+        int32_t *buf = nullptr;
+        size_t ints = 0;
+        int first = 0, count = 0;
+        bool pending = false, consumed_recorded = false;
+    } up[2];  // [0]: int32 imat, [1]: packed bits
     int last_levels = 0;
     bool measured = false;
     int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
     std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<int, int> auto_R;  // halo depth -> strip height chosen by choose_R
+    int n_sm = 148;
 };
 
 int mcrg_fail(int code, const char *fmt, ...) {
@@ -115,23 +121,64 @@ void mcrg_ctx_set_comm(mcrg_ctx *c, void *comm, void *limbs) {
 
 namespace {
 
-int choose_R(const mcrg_ctx *c, int H) {
+// Row steps a half-sweep over `nrows` rows costs a CTA of `threads` threads (the row distribution of mc_half_sweep_t): a thread
+// owns one column, the threads / W row groups take whole row pairs (W >= 32) or equal even chunks (W < 32).
+int half_sweep_steps(int nrows, int W, int threads) {
+    const int n_grp = threads / W > 0 ? threads / W : 1;
+    if (W >= 32) return 2 * ((nrows / 2 + n_grp - 1) / n_grp);
+    const int chunk = (nrows + n_grp - 1) / n_grp;
+    return (chunk + 1) & ~1;
+}
+
+// Estimated duration of one k_sweep0<MEASURE> launch with strips of R rows, in row steps of one SM.  The kernel is bound by
+// instruction issue, so a CTA costs its row steps (plus the measurement at ~0.6 of a row step per pair row of a thread and a
+// fixed part: staging, barriers, the queue pass and the set-up of every half-sweep), an SM issues at a rate that grows with the
+// resident warps up to the 24 the register budget allows, and the CTAs are handed out in waves of n_sm x occupancy — the last
+// wave is as slow as its fullest SM.  What this captures: wave quantisation (C5: 1024 CTAs of 16 rows on 444 slots = 3 waves
+// for 2.3 waves of work), idle row groups in short strips, halo rows.  Calibrated on profiles/r2/strip_rows_scan.txt.
+double sweep0_cost(const mcrg_ctx *c, int R, int H, int nsw) {
     const int L = c->L, W = c->W;
+    const int threads = sweep0_threads(L, R, H), occ = sweep0_occupancy(L, R, H);
+    if (occ < 1) return 1e300;
+    const int rows = R + 2 * H;
+    double work = 3.0;
+    for (int h = 0; h < 2 * (nsw > 0 ? nsw : 0); ++h) work += 1.0 + half_sweep_steps(rows - 2 - 2 * h, W, threads);
+    const int di = threads / W > 0 ? threads / W : 1;
+    work += 0.6 * ((R / 2 + di - 1) / di);
+    auto rate = [&](int n_ctas_on_sm) { const double r = 0.1 + 0.0375 * (n_ctas_on_sm * threads / 32.0); return r < 1.0 ? r : 1.0; };
+    const long long ctas = (long long)c->n_replicas * ((L + R - 1) / R), slots = (long long)c->n_sm * occ;
+    const long long full = ctas / slots, rest = ctas % slots;
+    double t = (double)full * occ / rate(occ);
+    if (rest > 0) {
+        const int per_sm = (int)((rest + c->n_sm - 1) / c->n_sm);
+        t += per_sm / rate(per_sm);
+    }
+    return t * work;
+}
+
+// Rows per strip: the explicit setting (mcrg_set_tuning / MCRG_STRIP_ROWS) if it fits, else the even height with the lowest
+// estimated launch time (sweep0_cost); cached per halo depth, the choice does not change during the life of a context.
+int choose_R(mcrg_ctx *c, int H) {
+    const int L = c->L;
     const int max_smem = sweep0_max_smem();
     auto fits = [&](int R) { return (long long)sweep0_smem_bytes(L, R, H) <= (long long)max_smem; };
-    if (c->strip_rows >= 2 && c->strip_rows <= L && is_pow2(c->strip_rows) && fits(c->strip_rows)) return c->strip_rows;
-    // Rows per strip.  A half-sweep hands the R+2 / R rows of a strip to blockDim/W row groups in equal chunks (even ones
-    // when a warp spans several rows, W < 32): 64 rows suit W >= 32; with W = 16 (L = 1024) 66 rows over 16 groups cost
-    // 6 steps for 4.1 rows' worth of work, 130 rows cost 10 for 8.1 — taller strips waste fewer steps.
-    int R = 4096 / W;
-    const int cap = W <= 16 ? 128 : 64;
-    if (R > cap) R = cap;
-    if (R < 16) R = 16;
-    if (R > L) R = L;
-    while (R > 2 && !fits(R)) R >>= 1;
-    // keep every SM busy: at least two CTAs per SM when the batch is small
-    while (R > 8 && (long long)c->n_replicas * (L / R) < 2 * 148) R >>= 1;
-    return R;
+    if (c->strip_rows >= 2 && c->strip_rows <= L && (c->strip_rows & 1) == 0 && fits(c->strip_rows)) return c->strip_rows;
+    auto it = c->auto_R.find(H);
+    if (it != c->auto_R.end()) return it->second;
+    const int nsw = H / 2;  // callers stage H = 2 * (sweeps fused per launch) halo rows (2 for a measurement without a sweep)
+    int best = 2;
+    double best_cost = 1e300;
+    for (int R = 2; R <= L && R <= 256; R += 2) {
+        if (!fits(R)) break;
+        if (L % R != 0 && (L / R) < 8) continue;  // a ragged last strip is fine among many strips, wasteful among few
+        const double cost = sweep0_cost(c, R, H, nsw);
+        if (cost < best_cost * (1.0 - 1e-9)) {
+            best_cost = cost;
+            best = R;
+        }
+    }
+    c->auto_R[H] = best;
+    return best;
 }
 
 int choose_Rn(int Ln) {
@@ -178,15 +225,17 @@ SweepArgs sweep_args(const mcrg_ctx *c, int R, int nsw, unsigned long long t_off
     a.R = R;
     a.H = nsw > 0 ? 2 * nsw : 2;
     a.nsw = nsw;
-    a.strips = c->L / R;
+    a.strips = (c->L + R - 1) / R;
     return a;
 }
 
 // enqueue nsw sweeps (no measurement), fused `fuse` per launch; flips c->cur per launch
 void enqueue_sweeps(mcrg_ctx *c, int n, unsigned long long t_off) {
     int done = 0;
+    int fuse = c->fuse_sweeps;  // the halo of k fused sweeps is 2k rows on each side: fuse only as deep as shared memory allows
+    while (fuse > 1 && (long long)sweep0_smem_bytes(c->L, 2, 2 * fuse) > (long long)sweep0_max_smem()) --fuse;
     while (done < n) {
-        const int k = (n - done) < c->fuse_sweeps ? (n - done) : c->fuse_sweeps;
+        const int k = (n - done) < fuse ? (n - done) : fuse;
         const int R = choose_R(c, 2 * k);
         SweepArgs a = sweep_args(c, R, k, t_off + done);
         launch_sweep0(a, c->n_replicas, false, c->stream);
@@ -279,7 +328,6 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     ta.S_out = c->S_out;
     ta.acc_lo = c->acc_lo;
     ta.acc_hi = c->acc_hi;
-    ta.acc_d = c->acc_d;
     ta.d_t = c->d_t;
     ta.t_off = t_off;
     ta.seed = c->seed;
@@ -345,7 +393,6 @@ void enqueue_resident_launch(mcrg_ctx *c, bool measure, int n_samples, int m, in
     a.bin = bin;
     a.acc_lo = c->acc_lo;
     a.acc_hi = c->acc_hi;
-    a.acc_d = c->acc_d;
     a.S_out = c->S_out;
     launch_resident(a, c->n_replicas, measure, c->resident_threads, c->stream);
 }
@@ -402,11 +449,18 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     c->seed = seed;
     c->replica_base = replica_base;
     c->full_levels = ilog2h(L) - 1;  // mcrg.cpp:43; 0 for the 2x2 lattice
-    if (const char *e = getenv("MCRG_STRIP_ROWS")) c->strip_rows = atoi(e);
-    if (const char *e = getenv("MCRG_FUSE_SWEEPS")) c->fuse_sweeps = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("MCRG_STRIP_ROWS")) {  // same rules as mcrg_set_tuning; anything else is ignored
+        const int v = atoi(e);
+        if (v >= 2 && v <= L && (v & 1) == 0) c->strip_rows = v;
+    }
+    if (const char *e = getenv("MCRG_FUSE_SWEEPS")) {
+        const int v = atoi(e);
+        c->fuse_sweeps = v < 1 ? 1 : (v > 8 ? 8 : v);
+    }
     if (const char *e = getenv("MCRG_USE_GRAPHS")) c->use_graphs = atoi(e);
     *out = c;  // so that a failure below can still be cleaned up by mcrg_ctx_destroy
     sweep0_max_smem();  // opt in to large dynamic shared memory once, outside any stream capture
+    CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     {
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -450,7 +504,6 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     const size_t n_acc = (size_t)n_replicas * n_bins * N_SLOTS;
     CK(cudaMalloc(&c->acc_lo, n_acc * 8));
     CK(cudaMalloc(&c->acc_hi, n_acc * 8));
-    CK(cudaMalloc(&c->acc_d, (size_t)n_replicas * n_bins * N_DSLOTS * 8));
     CK(cudaMalloc(&c->T4, n_replicas * 4));
     CK(cudaMalloc(&c->T8, n_replicas * 4));
     CK(cudaMalloc(&c->anti, n_replicas * 4));
@@ -492,7 +545,6 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->S_out);
     cudaFree(c->acc_lo);
     cudaFree(c->acc_hi);
-    cudaFree(c->acc_d);
     cudaFree(c->T4);
     cudaFree(c->T8);
     cudaFree(c->anti);
@@ -505,11 +557,13 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     cudaFree(c->rgnn_u);
     cudaFree(c->rgnn_grad);
     cudaFree(c->stage);
-    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    cudaFree(c->upload);
-    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
-    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
-    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto &u : c->up) {
+        if (u.stream) cudaStreamSynchronize(u.stream);
+        cudaFree(u.buf);
+        if (u.ev_copy) cudaEventDestroy(u.ev_copy);
+        if (u.ev_consumed) cudaEventDestroy(u.ev_consumed);
+        if (u.stream) cudaStreamDestroy(u.stream);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int p = 0; p < 2; ++p) {
@@ -549,13 +603,33 @@ int mcrg_timer_stop(mcrg_ctx *c, float *ms) {
 
 int mcrg_set_tuning(mcrg_ctx *c, int strip_rows, int fuse_sweeps, int use_graphs) {
     if (!c) return fail(MCRG_ERR_ARG, "null context");
-    if (strip_rows != 0 && (!is_pow2(strip_rows) || strip_rows < 2 || strip_rows > c->L))
-        return fail(MCRG_ERR_ARG, "strip_rows=%d must be 0 or a power of two in [2, L]", strip_rows);
+    if (strip_rows != 0 && ((strip_rows & 1) || strip_rows < 2 || strip_rows > c->L))
+        return fail(MCRG_ERR_ARG, "strip_rows=%d must be 0 or an even number in [2, L]", strip_rows);
     if (fuse_sweeps < 1 || fuse_sweeps > 8) return fail(MCRG_ERR_ARG, "fuse_sweeps=%d must be in [1, 8]", fuse_sweeps);
     c->strip_rows = strip_rows;
     c->fuse_sweeps = fuse_sweeps;
     c->use_graphs = use_graphs;
+    c->auto_R.clear();
     destroy_graphs(c);
+    return 0;
+}
+
+int mcrg_strip_plan(mcrg_ctx *c, int fused_sweeps, int strip_rows, int *rows_out, double *cost_out) {
+    if (!c) return fail(MCRG_ERR_ARG, "null context");
+    if (fused_sweeps < 1 || fused_sweeps > 8) return fail(MCRG_ERR_ARG, "fused_sweeps=%d must be in [1, 8]", fused_sweeps);
+    CK(cudaSetDevice(c->device));
+    const int H = 2 * fused_sweeps;
+    int R = strip_rows;
+    if (R == 0) {  // the automatic choice, whatever mcrg_set_tuning fixed
+        const int keep = c->strip_rows;
+        c->strip_rows = 0;
+        R = choose_R(c, H);
+        c->strip_rows = keep;
+    } else if ((R & 1) || R < 2 || R > c->L) {
+        return fail(MCRG_ERR_ARG, "strip_rows=%d must be 0 or an even number in [2, L]", R);
+    }
+    if (rows_out) *rows_out = R;
+    if (cost_out) *cost_out = (long long)sweep0_smem_bytes(c->L, R, H) <= (long long)sweep0_max_smem() ? sweep0_cost(c, R, H, fused_sweeps) : -1.0;
     return 0;
 }
 
@@ -651,83 +725,65 @@ int mcrg_set_spins_packed(mcrg_ctx *c, int first, int count, const uint32_t *pac
     return 0;
 }
 
-int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *c, int first, int count, const int32_t *pinned_host) {
-    if (!c || !pinned_host) return fail(MCRG_ERR_ARG, "null pointer");
-    if (first < 0 || count < 1 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
-    if (c->up_pending) return fail(MCRG_ERR_STATE, "an upload is already in flight: call mcrg_set_spins_commit first");
+// start copying `ints` 32-bit words from pinned host memory into lane `k`'s device buffer on that lane's copy stream
+static int upload_begin(mcrg_ctx *c, int k, int first, int count, const void *pinned_host, size_t ints) {
+    mcrg_ctx::UploadLane &u = c->up[k];
+    if (u.pending) return fail(MCRG_ERR_STATE, "an upload of this kind is already in flight: call mcrg_set_spins_commit first");
     CK(cudaSetDevice(c->device));
-    const size_t ints = (size_t)count * c->L * c->L;
-    if (!c->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    if (!u.stream) {
+        CK(cudaStreamCreateWithFlags(&u.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&u.ev_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&u.ev_consumed, cudaEventDisableTiming));
     }
-    if (c->upload_ints < ints) {
-        CK(cudaStreamSynchronize(c->copy_stream));
+    if (u.ints < ints) {
+        CK(cudaStreamSynchronize(u.stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (c->upload) cudaFree(c->upload);
-        c->upload = nullptr;
-        c->upload_ints = 0;
-        CK(cudaMalloc(&c->upload, ints * sizeof(int32_t)));
-        c->upload_ints = ints;
-        c->up_packed_recorded = false;
+        if (u.buf) cudaFree(u.buf);
+        u.buf = nullptr;
+        u.ints = 0;
+        CK(cudaMalloc(&u.buf, ints * sizeof(int32_t)));
+        u.ints = ints;
+        u.consumed_recorded = false;
     }
-    // the previous commit's pack kernel must have consumed the buffer before it is overwritten
-    if (c->up_packed_recorded) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed, 0));
-    CK(cudaMemcpyAsync(c->upload, pinned_host, ints * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
-    CK(cudaEventRecord(c->ev_copy, c->copy_stream));
-    c->up_first = first;
-    c->up_count = count;
-    c->up_pending = true;
+    // the previous commit's unpack kernel must have consumed the buffer before it is overwritten
+    if (u.consumed_recorded) CK(cudaStreamWaitEvent(u.stream, u.ev_consumed, 0));
+    CK(cudaMemcpyAsync(u.buf, pinned_host, ints * sizeof(int32_t), cudaMemcpyHostToDevice, u.stream));
+    CK(cudaEventRecord(u.ev_copy, u.stream));
+    u.first = first;
+    u.count = count;
+    u.pending = true;
     return 0;
 }
 
-// The same for configurations already packed on the host (mcrg_host_pack_i32_colmajor): 1 bit per spin over PCIe, on the
-// copy stream, overlapping whatever the context's stream is running.
+int mcrg_set_spins_i32_colmajor_begin(mcrg_ctx *c, int first, int count, const int32_t *pinned_host) {
+    if (!c || !pinned_host) return fail(MCRG_ERR_ARG, "null pointer");
+    if (first < 0 || count < 1 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
+    return upload_begin(c, 0, first, count, pinned_host, (size_t)count * c->L * c->L);
+}
+
+// The same for configurations already packed on the host (mcrg_host_pack_i32_colmajor): 1 bit per spin over PCIe.
 int mcrg_set_spins_packed_begin(mcrg_ctx *c, int first, int count, const uint32_t *pinned_host_packed) {
     if (!c || !pinned_host_packed) return fail(MCRG_ERR_ARG, "null pointer");
     if (first < 0 || count < 1 || first + count > c->n_replicas) return fail(MCRG_ERR_ARG, "replica range [%d, %d) out of [0, %d)", first, first + count, c->n_replicas);
-    if (c->up_pending) return fail(MCRG_ERR_STATE, "an upload is already in flight: call mcrg_set_spins_commit first");
-    CK(cudaSetDevice(c->device));
-    const size_t words = mcrg_packed_words(c->L, count);
-    if (!c->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
-    }
-    if (c->upload_ints < words) {
-        CK(cudaStreamSynchronize(c->copy_stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (c->upload) cudaFree(c->upload);
-        c->upload = nullptr;
-        c->upload_ints = 0;
-        CK(cudaMalloc(&c->upload, words * sizeof(int32_t)));
-        c->upload_ints = words;
-        c->up_packed_recorded = false;
-    }
-    if (c->up_packed_recorded) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed, 0));
-    CK(cudaMemcpyAsync(c->upload, pinned_host_packed, words * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CK(cudaEventRecord(c->ev_copy, c->copy_stream));
-    c->up_first = first;
-    c->up_count = count;
-    c->up_pending = true;
-    c->up_is_packed = true;
-    return 0;
+    return upload_begin(c, 1, first, count, pinned_host_packed, mcrg_packed_words(c->L, count));
 }
 
 int mcrg_set_spins_commit(mcrg_ctx *c) {
     if (!c) return fail(MCRG_ERR_ARG, "null context");
-    if (!c->up_pending) return fail(MCRG_ERR_STATE, "no upload in flight");
+    if (!c->up[0].pending && !c->up[1].pending) return fail(MCRG_ERR_STATE, "no upload in flight");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-    uint32_t *dst = c->planes[c->cur] + (size_t)c->up_first * 2 * c->L * c->W;
-    if (c->up_is_packed) launch_pack_nat(reinterpret_cast<const uint32_t *>(c->upload), dst, c->L, c->up_count, c->stream);
-    else launch_pack0(c->upload, dst, c->L, c->up_count, c->stream);
-    c->up_is_packed = false;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev_packed, c->stream));
-    c->up_packed_recorded = true;
-    c->up_pending = false;
+    for (int k = 0; k < 2; ++k) {
+        mcrg_ctx::UploadLane &u = c->up[k];
+        if (!u.pending) continue;
+        CK(cudaStreamWaitEvent(c->stream, u.ev_copy, 0));
+        uint32_t *dst = c->planes[c->cur] + (size_t)u.first * 2 * c->L * c->W;
+        if (k == 1) launch_pack_nat(reinterpret_cast<const uint32_t *>(u.buf), dst, c->L, u.count, c->stream);
+        else launch_pack0(u.buf, dst, c->L, u.count, c->stream);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(u.ev_consumed, c->stream));
+        u.consumed_recorded = true;
+        u.pending = false;
+    }
     return 0;
 }
 
@@ -851,6 +907,8 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
         return 0;
     }
     int done = 0;
+    choose_R(c, 2);  // strip heights are chosen (occupancy queries) before any stream capture starts
+    for (int k = 1; k <= c->fuse_sweeps; ++k) choose_R(c, 2 * k);
     if (c->use_graphs) {
         const int chunk = 16;
         while (n_samples - done >= chunk) {
@@ -994,7 +1052,6 @@ int mcrg_rgnn_accumulators_get(mcrg_ctx *c, double *out) {
 int mcrg_accumulators_layout(mcrg_acc_layout *o) {
     if (!o) return fail(MCRG_ERR_ARG, "null pointer");
     o->n_slots = N_SLOTS;
-    o->n_dslots = N_DSLOTS;
     o->slot_n = SLOT_N;
     o->slot_absm = SLOT_ABSM;
     o->slot_m2 = SLOT_M2;
@@ -1002,7 +1059,7 @@ int mcrg_accumulators_layout(mcrg_acc_layout *o) {
     o->slot_ss = SLOT_SS;
     o->slot_sbs = SLOT_SBS;
     o->slot_sb0 = SLOT_SB0;
-    o->dslot_m4 = 0;
+    o->slot_m4 = SLOT_M4;
     return 0;
 }
 
@@ -1012,17 +1069,15 @@ int mcrg_accumulators_reset(mcrg_ctx *c) {
     const size_t n_acc = (size_t)c->n_replicas * c->n_bins * N_SLOTS;
     CK(cudaMemsetAsync(c->acc_lo, 0, n_acc * 8, c->stream));
     CK(cudaMemsetAsync(c->acc_hi, 0, n_acc * 8, c->stream));
-    CK(cudaMemsetAsync(c->acc_d, 0, (size_t)c->n_replicas * c->n_bins * N_DSLOTS * 8, c->stream));
     return 0;
 }
 
-int mcrg_accumulators_get(mcrg_ctx *c, int64_t *hi, uint64_t *lo, double *d) {
+int mcrg_accumulators_get(mcrg_ctx *c, int64_t *hi, uint64_t *lo) {
     if (!c) return fail(MCRG_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     const size_t n_acc = (size_t)c->n_replicas * c->n_bins * N_SLOTS;
     if (hi) CK(cudaMemcpyAsync(hi, c->acc_hi, n_acc * 8, cudaMemcpyDeviceToHost, c->stream));
     if (lo) CK(cudaMemcpyAsync(lo, c->acc_lo, n_acc * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (d) CK(cudaMemcpyAsync(d, c->acc_d, (size_t)c->n_replicas * c->n_bins * N_DSLOTS * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -456,14 +456,24 @@ __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R,
     const uint32_t dq = (uint32_t)(di << lw);
     MeasureAcc m = {0u, 0u, 0u, 0u};
     const int half = R >> 1;
-    if (FAST4 && blockDim.x == 256 && (half & (4 * di - 1)) == 0) {
-        // Every thread has a multiple of four items, 256 output words apart, the first with bits 8-9 of q clear (q = 1024 k +
-        // threadIdx.x): exactly the four words that share one tie-coin call (tie_group), in the order x, y, z, w.
-        for (int i = i0; i < half; i += 4 * di, q += 1024u) {
+    if (FAST4 && blockDim.x == 256) {
+        // The CTA's 256 threads x 4 items cover one 1024-word chunk of level-1 output (4 * di pair rows): a thread's items are
+        // the words q = 1024 c + threadIdx.x + 256 e, e = 0..3 — exactly the four words that share one tie-coin call
+        // (tie_group), in the order x, y, z, w.  Chunks are aligned to the LATTICE (not to the strip), so a strip of any even
+        // height and any first row works: items whose pair row falls outside the strip are skipped (strip edges only; the
+        // test is warp-uniform for W >= 32).
+        const int P0 = y0 >> 1, chunk = 4 * di;
+        const int c_first = P0 / chunk, c_last = (P0 + half - 1) / chunk;
+        int pl = c_first * chunk + i0 - P0;  // this thread's pair row relative to the strip; may start negative
+        pb += 2 * (pl - i0) * W;             // (not dereferenced while out of range)
+        pw += 2 * (pl - i0) * W;
+        q = (uint32_t)(c_first * 1024) + threadIdx.x;
+        for (int c = c_first; c <= c_last; ++c, q += 1024u) {
             const U4 r = philox_keyed(seed, tie_group(q), replica, t, PURPOSE_TIE, 1);
             const uint32_t coin[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e, pb += step, pw += step) {
+            for (int e = 0; e < 4; ++e, pb += step, pw += step, pl += di) {
+                if ((unsigned)pl >= (unsigned)half) continue;
                 uint32_t tie;
                 const uint32_t maj = measure_item_b32<WT>(pb, pw, W, d_up, d_dn, m, tie);
                 lev1[q + 256u * e] = maj | (tie & coin[e]);
@@ -541,8 +551,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.y, strip = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
-    const int rows = a.R + 2 * a.H;
     const int y0 = strip * a.R;
+    const int Rs = min(a.R, L - y0);  // R need not divide L: the last strip takes what is left (even, like R and L)
+    const int rows = Rs + 2 * a.H;
     Strip0 s;
     s.base = smem;
     s.rows = rows;
@@ -570,11 +581,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
 
     if (MEASURE) {
         Counts c = {0u, 0u, 0u, 0u};
-        const int npairs = (a.R >> 1) << lw;
+        const int npairs = (Rs >> 1) << lw;
         uint32_t *lev1 = a.level1 + (size_t)r * (L >> 1) * W;
         if (a.bits == 32) {  // L >= 64
-            if (W == 64) measure_strip_b32<64, true>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);  // L = 4096
-            else measure_strip_b32<0, true>(s, a.H, a.R, lw, y0, lev1, a.seed, replica, t, c);
+            if (W == 64) measure_strip_b32<64, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c);  // L = 4096
+            else measure_strip_b32<0, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c);
         } else {
             TieCache coins;
             coins.init();
@@ -607,14 +618,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
             fence_proxy_async();  // this thread's shared-memory writes become visible to the copy engine ...
             __syncthreads();      // ... and so do everybody else's
             if (threadIdx.x == 0) {
-                const uint32_t bytes = (uint32_t)a.R * (uint32_t)W * 4u;
+                const uint32_t bytes = (uint32_t)Rs * (uint32_t)W * 4u;
                 bulk_s2g(dst_r + (size_t)y0 * W, s0_plane(s, 0) + a.H * W, bytes);
                 bulk_s2g(dst_r + (size_t)L * W + (size_t)y0 * W, s0_plane(s, 1) + a.H * W, bytes);
                 bulk_commit_wait_read();  // shared memory must stay alive until the engine has read it
             }
         } else {
-            unstage_rows(dst_r, s0_plane(s, 0) + a.H * W, y0, a.R, W, L);
-            unstage_rows(dst_r + (size_t)L * W, s0_plane(s, 1) + a.H * W, y0, a.R, W, L);
+            unstage_rows(dst_r, s0_plane(s, 0) + a.H * W, y0, Rs, W, L);
+            unstage_rows(dst_r + (size_t)L * W, s0_plane(s, 1) + a.H * W, y0, Rs, W, L);
         }
     }
 }
@@ -788,10 +799,12 @@ __device__ __forceinline__ void add128(unsigned long long *lo, long long *hi, __
 // The accumulator slots that are live for a pyramid of n_levels blocking levels, in a compact order:
 // k -> (slot index in the public layout, this sample's contribution).  S_sh[lv*4 + {nn, nnn, plaq, sum}].
 // mcrg.cpp:86-97 with the column-major flatten of definitions.cpp:9-19 (index b*NOP+a holds X_a * Y_b).
-__device__ __forceinline__ int acc_live_slots(int n_levels) { return 3 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels; }
+constexpr int ACC_FIXED = 6;  // N, |M|, M^2 and the three M^4 parts
+__device__ __forceinline__ int acc_live_slots(int n_levels) { return ACC_FIXED + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels; }
 
-// Slot k contributes X[ia] * X[ib] per sample, X being S_sh extended by two pseudo-entries: X_ONE = 1 and X_ABSM = |M|.
-constexpr int X_ONE = (MAX_LEVELS + 1) * 4, X_ABSM = X_ONE + 1, X_LEN = X_ABSM + 1;
+// Slot k contributes X[ia] * X[ib] per sample, X being S_sh extended by pseudo-entries: X_ONE = 1, X_ABSM = |M|, and the two
+// halves of M^2 = X_M2H * 2^20 + X_M2L (the exact sum of M^4 is kept as the three products of the halves, see SLOT_M4).
+constexpr int X_ONE = (MAX_LEVELS + 1) * 4, X_ABSM = X_ONE + 1, X_M2H = X_ABSM + 1, X_M2L = X_M2H + 1, X_LEN = X_M2L + 1;
 
 __device__ __forceinline__ void acc_slot_decode(int k, int n_levels, int &slot, int &ia, int &ib) {
     if (k < 3) {
@@ -800,7 +813,13 @@ __device__ __forceinline__ void acc_slot_decode(int k, int n_levels, int &slot, 
         ib = k == 2 ? 3 : X_ONE;
         return;
     }
-    k -= 3;
+    if (k < ACC_FIXED) {
+        slot = SLOT_M4 + (k - 3);  // h*h, h*l, l*l
+        ia = k == 5 ? X_M2L : X_M2H;
+        ib = k == 3 ? X_M2H : X_M2L;
+        return;
+    }
+    k -= ACC_FIXED;
     if (k < NOP * (n_levels + 1)) {
         const int lv = k / NOP, op = k - lv * NOP;
         slot = SLOT_S + lv * NOP + op;
@@ -828,6 +847,8 @@ __device__ __forceinline__ void acc_slot_decode(int k, int n_levels, int &slot, 
 __device__ __forceinline__ long long acc_x(const long long *S_sh, int i) {
     if (i == X_ONE) return 1;
     if (i == X_ABSM) return S_sh[3] < 0 ? -S_sh[3] : S_sh[3];
+    if (i == X_M2H) return (S_sh[3] * S_sh[3]) >> M4_SPLIT_BITS;  // |M| <= 2^28: M^2 fits
+    if (i == X_M2L) return (S_sh[3] * S_sh[3]) & ((1ll << M4_SPLIT_BITS) - 1);
     return S_sh[i];
 }
 
@@ -884,10 +905,6 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
         __int128 v;
         acc_slot_value(k, a.n_levels, S_sh, slot, v);
         add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], v);
-    }
-    if (threadIdx.x == 0) {
-        const double m = (double)S_sh[3];
-        a.acc_d[((size_t)r * a.n_bins + a.bin) * N_DSLOTS + 0] += m * m * m * m;
     }
 }
 
@@ -951,7 +968,6 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
         }
     if (threadIdx.x == 0) S_sh[X_ONE] = 1;
     const uint32_t anti = a.anti[r];
-    double m4 = 0.0;
     tile_stage_wait(tma, &bar);
     __syncthreads();
 
@@ -985,17 +1001,17 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
                 long long S[4];
                 counts_to_S((long long)(L >> lv), red[lv * 4 + 0], red[lv * 4 + 1], red[lv * 4 + 2], red[lv * 4 + 3], S);
                 for (int k = 0; k < 4; ++k) S_sh[lv * 4 + k] = S[k];
-                if (lv == 0) S_sh[X_ABSM] = S[3] < 0 ? -S[3] : S[3];
+                if (lv == 0) {
+                    S_sh[X_ABSM] = S[3] < 0 ? -S[3] : S[3];
+                    S_sh[X_M2H] = (S[3] * S[3]) >> M4_SPLIT_BITS;
+                    S_sh[X_M2L] = (S[3] * S[3]) & ((1ll << M4_SPLIT_BITS) - 1);
+                }
             }
             __syncthreads();
             if (a.accumulate) {
                 for (int k = threadIdx.x; k < n_live; k += blockDim.x) {
                     const int e = dec[k].y;
                     acc64[k] += S_sh[e & 255] * S_sh[e >> 8];
-                }
-                if (threadIdx.x == 0) {
-                    const double m = (double)S_sh[3];
-                    m4 += m * m * m * m;
                 }
             }
             // S_sh / red are rewritten only after the barriers inside the sweeps below (or at the loop top)
@@ -1027,7 +1043,6 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
                 const int slot = dec[k].x;
                 add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], (__int128)acc64[k]);
             }
-            if (threadIdx.x == 0) a.acc_d[((size_t)r * a.n_bins + a.bin) * N_DSLOTS + 0] += m4;
         }
     }
 }
@@ -1054,6 +1069,18 @@ size_t sweep0_smem_bytes(int L, int R, int H) {
     const int words = (R + 2 * H) * l0_words(L);
     const int warps = sweep0_threads(L, R, H) / 32;
     return ((((size_t)2 * words + 3) & ~(size_t)3) + (size_t)4 * warps * sweep0_queue_cap(words, warps)) * sizeof(uint32_t);
+}
+
+// resident k_sweep0 CTAs per SM for a strip geometry (registers: at most MCRG_SWEEP_MIN_BLOCKS x 256 threads; shared memory)
+int sweep0_occupancy(int L, int R, int H) {
+    sweep0_max_smem();
+    int n = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sweep0<true>, sweep0_threads(L, R, H), sweep0_smem_bytes(L, R, H));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 int sweep0_max_smem() {

@@ -29,8 +29,12 @@ constexpr int SLOT_SS = SLOT_S + NOP * (MAX_LEVELS + 1);     // + lv*9 + b*3 + a
 constexpr int SLOT_SBS = SLOT_SS + NOP * NOP * (MAX_LEVELS + 1);  // + (n-1)*9 + b*3 + a  sum S^(n)_a S^(n-1)_b
 constexpr int SLOT_SB0 = SLOT_SBS + NOP * NOP * MAX_LEVELS;       // + (n-1)*9 + b*3 + a  sum S^(n)_a S^(0)_b  (two-lattice
                                                                   //   matching needs S(blocked) x S(level 0), mcrg.cpp:262-263)
-constexpr int N_SLOTS = SLOT_SB0 + NOP * NOP * MAX_LEVELS;
-constexpr int N_DSLOTS = 1;  // double slots: sum M^4
+// sum M^4, exact: M^2 = h * 2^20 + l (l < 2^20), three slots sum h*h, sum h*l, sum l*l;  sum M^4 = HH * 2^40 + 2 * HL * 2^20 + LL.
+// (M^4 reaches 2^112 at L = 16384 — one 128-bit slot would overflow after 2^15 ordered samples — and k_resident sums a launch
+// in 64 bits: with L <= 512, h <= 2^16 and every product stays below 2^40 like the correlator products.)
+constexpr int SLOT_M4 = SLOT_SB0 + NOP * NOP * MAX_LEVELS;        // + {0: h*h, 1: h*l, 2: l*l}
+constexpr int N_SLOTS = SLOT_M4 + 3;
+constexpr int M4_SPLIT_BITS = 20;
 
 struct SweepArgs {
     const uint32_t *src;       // planes [replica][colour][y][w]
@@ -44,7 +48,7 @@ struct SweepArgs {
     uint32_t replica_base;
     int L, W, bits;
     int R, H, nsw;
-    int strips;                // L / R
+    int strips;                // ceil(L / R): the last strip may be shorter
 };
 
 struct LevelArgs {
@@ -67,7 +71,6 @@ struct TailArgs {
     long long *S_out;          // [replica][MAX_LEVELS+1][4] converted sums of the last measurement
     unsigned long long *acc_lo;
     long long *acc_hi;
-    double *acc_d;
     const unsigned long long *d_t;
     unsigned long long t_off;
     uint64_t seed;
@@ -93,7 +96,6 @@ struct ResidentArgs {
     int n_levels, accumulate, n_bins, bin;
     unsigned long long *acc_lo;
     long long *acc_hi;
-    double *acc_d;
     long long *S_out;
 };
 
@@ -110,7 +112,7 @@ MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
     const int L1 = L / 2 > 0 ? L / 2 : 1, L2 = L / 4 > 0 ? L / 4 : 1;
     o.bufB_off = (o.bufA_off + L1 * nat_words(L1) + 3) & ~3;
     o.acc_off = (o.bufB_off + L2 * nat_words(L2) + 3) & ~3;
-    const int n_live = 3 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels;
+    const int n_live = 6 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels;  // = acc_live_slots (kernels.cu)
     o.total_words = o.acc_off + 4 * n_live;
     return o;
 }
@@ -148,5 +150,6 @@ int probe_philox_rate(cudaStream_t st, double *calls_per_s);
 size_t sweep0_smem_bytes(int L, int R, int H);
 int sweep0_threads(int L, int R, int H);
 int sweep0_max_smem();
+int sweep0_occupancy(int L, int R, int H);
 
 }  // namespace mcrg

@@ -3,6 +3,8 @@
 //   mcrg_app kc L K0 n_iterations n_eq n_samples    -> MonteCarloRenormalizationGroup::locate_critical_point
 //   mcrg_app lattice N K n_updates                  -> Lattice / IsingModel fine-grained calls (prints observables)
 //   mcrg_app train L K n_cycles n_samples n_eq      -> RenormalizationGroupNeuralNetwork::train_scalar_output
+//   mcrg_app equilibrate N K n_eq                   -> IsingModel::equilibrate(lattice, n_eq, write = true): thermodynamics log
+//   mcrg_app test L K0 DeltaK n_samples n_eq        -> RenormalizationGroupNeuralNetwork::test_scalar_output (W0 of train.cpp)
 // Environment: MCRG_REPLICAS, MCRG_SWEEPS_PER_UPDATE, MCRG_SEED, MCRG_DEVICE, MCRG_QUIET.
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +28,7 @@ int main(int argc, char **argv) {
             MonteCarloRenormalizationGroup rg(2);
             const double Kc = rg.locate_critical_point(atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[2]), atof(argv[3]));
             printf("RESULT Kc %.10f\n", Kc);
+            for (size_t n = 0; n < rg.kcs_.size(); ++n) printf("RESULT level %zu Kc %.10f err %.10f\n", n, rg.kcs_[n], rg.kc_errors_[n]);
         } else if (!strcmp(argv[1], "lattice") && argc == 5) {
             const int N = atoi(argv[2]);
             const double K = atof(argv[3]);
@@ -53,6 +56,18 @@ int main(int argc, char **argv) {
             net.set_weights(W0);
             net.train_scalar_output(atoi(argv[2]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atof(argv[3]), 1e-4, 1e-3);
             printf("RESULT final_mse %.10e W %.10f %.10f %.10f %.10f\n", net.final_mse_, net.W_(0, 0), net.W_(0, 1), net.W_(1, 0), net.W_(1, 1));
+        } else if (!strcmp(argv[1], "equilibrate") && argc == 5) {
+            std::shared_ptr<Lattice> lat(new Lattice(atoi(argv[2])));
+            IsingModel ising(atof(argv[3]));
+            ising.equilibrate(lat, atoi(argv[4]), true);
+            printf("RESULT sum %lld\n", lat->sum_spins());
+        } else if (!strcmp(argv[1], "test") && argc == 7) {
+            mat W0(2, 2);
+            W0(0, 0) = 0.5; W0(0, 1) = -0.5; W0(1, 0) = 0.5; W0(1, 1) = -0.5;
+            RenormalizationGroupNeuralNetwork net(2);
+            net.set_weights(W0);
+            net.test_scalar_output(atoi(argv[2]), atoi(argv[5]), atoi(argv[6]), atof(argv[3]), atof(argv[4]));
+            printf("RESULT done\n");
         } else {
             fprintf(stderr, "bad arguments\n");
             return 2;

@@ -70,10 +70,14 @@ struct Settings {
     int device;             // MCRG_DEVICE
     std::uint64_t seed;     // MCRG_SEED
     int quiet;              // MCRG_QUIET: suppress banners
-    int cluster;            // MCRG_UPDATE=cluster: Swendsen-Wang updates (the reference's family, ising.cpp:87-155)
-                            // instead of Metropolis sweeps; sweeps_per_update then counts cluster updates
+    int cluster;            // MCRG_UPDATE: 1 = "cluster" (Swendsen-Wang updates, the reference's family, ising.cpp:87-155;
+                            // sweeps_per_update then counts cluster updates), 0 = "metropolis", -1 = unset: cluster
+                            // updates for N >= 32, Metropolis sweeps below
     int devices;            // MCRG_DEVICES: GPUs of this process that calc_critical_exponent spreads its chains over
                             // (devices 0..n-1; totals by one NCCL all-reduce, mcrg_allreduce_accumulators)
+    int compat;             // MCRG_COMPAT (default 1): keep the reference's arithmetic in the thermodynamics log — the
+                            // INTEGER division in calc_magnetization (ising.cpp:178) and the second division of the
+                            // per-spin energy by n_spins (ising.cpp:72); 0 = |sum s| / N^2 as a real number, no second division
 };
 Settings &settings();
 }  // namespace mcrg_b200
@@ -141,6 +145,8 @@ public:
 
     // results of the last calc_critical_exponent call (additions; the reference only prints them)
     std::vector<double> lambdas_, nus_, lambda_errors_;
+    // last approx_critical_point call: Kc per blocking level and its jackknife error over groups of chains
+    std::vector<double> kcs_, kc_errors_;
 
 private:
     int rank_;

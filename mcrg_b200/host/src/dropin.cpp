@@ -82,13 +82,19 @@ static long env_long(const char *name, long dflt) {
 Settings &settings() {
     static Settings s = {(int)env_long("MCRG_REPLICAS", 1024), (int)env_long("MCRG_SWEEPS_PER_UPDATE", 1),
                          (int)env_long("MCRG_DEVICE", 0), (std::uint64_t)env_long("MCRG_SEED", 12345),
-                         (int)env_long("MCRG_QUIET", 0), 0, 1};
+                         (int)env_long("MCRG_QUIET", 0), -1, 1, 1};
     static bool parsed = false;
     if (!parsed) {
         s.devices = (int)env_long("MCRG_DEVICES", 1);
         if (s.devices < 1) s.devices = 1;
+        // MCRG_UPDATE: "cluster" | "metropolis" | unset = auto (cluster updates — the reference's update family,
+        // ising.cpp:87-155 — for N >= 32, where one Metropolis sweep is far from one Wolff update: tau ~ L^2.17 sweeps;
+        // Metropolis sweeps below, where the resident kernel decorrelates a lattice in a few sweeps)
         const char *u = std::getenv("MCRG_UPDATE");
-        s.cluster = (u && (std::string(u) == "cluster" || std::string(u) == "sw")) ? 1 : 0;
+        s.cluster = -1;
+        if (u && (std::string(u) == "cluster" || std::string(u) == "sw")) s.cluster = 1;
+        if (u && std::string(u) == "metropolis") s.cluster = 0;
+        s.compat = (int)env_long("MCRG_COMPAT", 1);
         parsed = true;
     }
     if (s.replicas < 1) s.replicas = 1;
@@ -101,8 +107,9 @@ struct DeviceBatch {
     int L = 0, replicas = 0;
     DeviceBatch(int L_, int replicas_, std::uint32_t replica_base, int device = -1) : L(L_), replicas(replicas_) {
         ck(mcrg_ctx_create(device < 0 ? settings().device : device, L, replicas, settings().seed, replica_base, 1, &ctx), "mcrg_ctx_create");
-        if (settings().cluster) ck(mcrg_set_update(ctx, MCRG_UPDATE_CLUSTER), "mcrg_set_update");
+        if (use_cluster(L)) ck(mcrg_set_update(ctx, MCRG_UPDATE_CLUSTER), "mcrg_set_update");
     }
+    static bool use_cluster(int L) { return settings().cluster == 1 || (settings().cluster < 0 && L >= 32); }
     ~DeviceBatch() { mcrg_ctx_destroy(ctx); }
     DeviceBatch(const DeviceBatch &) = delete;
     DeviceBatch &operator=(const DeviceBatch &) = delete;
@@ -118,8 +125,13 @@ static std::uint32_t take_batch_base(int replicas) { return g_next_batch_base.fe
 // exact 128-bit accumulator -> long double (64-bit mantissa: ample for covariances of ~1e-3 relative size)
 static long double to_ld(std::int64_t hi, std::uint64_t lo) { return (long double)hi * 18446744073709551616.0L + (long double)lo; }
 
+typedef __int128 i128;
+static i128 to_i128(std::int64_t hi, std::uint64_t lo) { return ((i128)hi << 64) | (i128)lo; }
+static long double to_ld(i128 x) { return to_ld((std::int64_t)(x >> 64), (std::uint64_t)x); }
+
 struct Totals {
-    std::vector<long double> v;  // [n_slots], summed over replicas
+    std::vector<long double> v;  // [n_slots], summed over replicas (each one rounding of the exact total)
+    std::vector<i128> exact;     // the same totals as exact integers
     std::vector<std::vector<long double>> per_replica;
 };
 
@@ -129,16 +141,18 @@ static Totals fetch_totals(DeviceBatch &b) {
     const size_t n = (size_t)b.replicas * lay.n_slots;
     std::vector<std::int64_t> hi(n);
     std::vector<std::uint64_t> lo(n);
-    ck(mcrg_accumulators_get(b.ctx, hi.data(), lo.data(), nullptr), "mcrg_accumulators_get");
+    ck(mcrg_accumulators_get(b.ctx, hi.data(), lo.data()), "mcrg_accumulators_get");
     Totals t;
-    t.v.assign(lay.n_slots, 0.0L);
+    t.exact.assign(lay.n_slots, 0);
     t.per_replica.assign(b.replicas, std::vector<long double>(lay.n_slots));
     for (int r = 0; r < b.replicas; ++r)
         for (int s = 0; s < lay.n_slots; ++s) {
-            const long double x = to_ld(hi[(size_t)r * lay.n_slots + s], lo[(size_t)r * lay.n_slots + s]);
-            t.per_replica[r][s] = x;
-            t.v[s] += x;
-        }
+            const i128 x = to_i128(hi[(size_t)r * lay.n_slots + s], lo[(size_t)r * lay.n_slots + s]);
+            t.per_replica[r][s] = to_ld(x);
+            t.exact[s] += x;  // totals are formed in exact integers: a running long-double sum rounds at every step once a
+        }                     // slot exceeds 2^64 (N = 4096 after a few thousand samples, N = 16384 after ~32)
+    t.v.resize(lay.n_slots);
+    for (int s = 0; s < lay.n_slots; ++s) t.v[s] = to_ld(t.exact[s]);
     return t;
 }
 
@@ -170,21 +184,20 @@ struct DeviceGroup {
         Totals t;
         for (auto &p : parts) {
             Totals part = fetch_totals(*p);
-            if (t.v.empty()) t.v.assign(part.v.size(), 0.0L);
-            for (size_t s = 0; s < part.v.size(); ++s) t.v[s] += part.v[s];
+            if (t.exact.empty()) t.exact.assign(part.exact.size(), 0);
+            for (size_t s = 0; s < part.exact.size(); ++s) t.exact[s] += part.exact[s];
             for (auto &row : part.per_replica) t.per_replica.push_back(std::move(row));
         }
+        t.v.resize(t.exact.size());
+        for (size_t s = 0; s < t.exact.size(); ++s) t.v[s] = to_ld(t.exact[s]);
         if (parts.size() > 1) {  // the exact grand totals, reduced on the devices
             mcrg_acc_layout lay;
             ck(mcrg_accumulators_layout(&lay), "mcrg_accumulators_layout");
             std::vector<std::int64_t> hi(lay.n_slots);
             std::vector<std::uint64_t> lo(lay.n_slots);
             ck(mcrg_allreduce_accumulators((int)ctxs.size(), ctxs.data(), hi.data(), lo.data()), "mcrg_allreduce_accumulators");
-            for (int s = 0; s < lay.n_slots; ++s) {
-                const long double x = to_ld(hi[s], lo[s]);
-                if (x != t.v[s]) throw std::runtime_error("all-reduced totals differ from the sum of the per-chain sums");
-                t.v[s] = x;
-            }
+            for (int s = 0; s < lay.n_slots; ++s)  // exact integers on both sides: the collective is exact and order independent
+                if (to_i128(hi[s], lo[s]) != t.exact[s]) throw std::runtime_error("all-reduced totals differ from the sum of the per-chain sums");
         }
         return t;
     }
@@ -372,40 +385,58 @@ void IsingModel::equilibrate(std::shared_ptr<Lattice> pLattice, int n_samples_eq
         device_sweeps(*pLattice, K_, n_samples_eq);
         return;
     }
-    // ising.cpp:22-74: thermodynamics log at log-spaced iterations, same file name and row format; the averages
-    // are over processes (one here), and E (already per spin) is divided by n_spins_ once more when printed,
-    // exactly as the reference does (ising.cpp:72)
-    if (rank_ == 0) {
-        const std::string filename = "equilibrate_N_" + std::to_string(pLattice->N_) + "_K_" + get_rounded_str(K_, 7) + ".txt";
-        fptr_ = fopen(filename.c_str(), "w");
-        if (!fptr_) throw std::runtime_error("cannot open " + filename);
-        fprintf(fptr_, "# Nearest neighbor coupling K = %lf\n", K_);
-        fprintf(fptr_, "# Temperature T = %lf\n", -1 / K_);
-        fprintf(fptr_, "# Number of lattice sites = %i\n", pLattice->N_ * pLattice->N_);
-        fprintf(fptr_, "# Lattice spacing = %i\n", pLattice->a_);
-        fprintf(fptr_, "# Using %i parallel processes\n", n_processes_);
-        fprintf(fptr_, "# %s, %s, %s, %s, %s, %s, %s\n", "Iteration", "Avg E/spin", "Stddev E/spin", "Heat Capacity",
-                "Avg |M|/spin", "Stddev |M|/spin", "Susceptibility");
-    }
+    // ising.cpp:22-74: thermodynamics log at log-spaced iterations, same file name and row format.  The reference averages
+    // E, |M|, E^2, M^2 over its MPI ranks (MPI_Reduce, ising.cpp:50-53), every rank running its own chain; here the ranks
+    // are MCRG_REPLICAS chains on the device: chain 0 is the caller's lattice, the others start hot like `Lattice(N)` on the
+    // other ranks would (lattice.cpp:33-41).  Between two logged iterations the chains advance in one call; a logged
+    // iteration is one level-0 measurement of all chains (exact integers S_nn, sum s), reduced on the host in the
+    // reference's formulas.  MCRG_COMPAT=1 (default) keeps the reference's arithmetic, see Settings::compat.
+    const int R = std::max(1, settings().replicas);
+    const int N = pLattice->N_, spu = settings().sweeps_per_update;
+    const bool compat = settings().compat != 0;
+    DeviceBatch batch(N, R, mcrg_b200::take_batch_base(R));
+    ck(mcrg_set_couplings(batch.ctx, &K_, 1), "mcrg_set_couplings");
+    ck(mcrg_init_hot(batch.ctx), "mcrg_init_hot");
+    ck(mcrg_set_spins_i32_colmajor(batch.ctx, 0, 1, pLattice->spins_.data()), "mcrg_set_spins_i32_colmajor");
+    const std::string filename = "equilibrate_N_" + std::to_string(N) + "_K_" + get_rounded_str(K_, 7) + ".txt";
+    fptr_ = fopen(filename.c_str(), "w");
+    if (!fptr_) throw std::runtime_error("cannot open " + filename);
+    fprintf(fptr_, "# Nearest neighbor coupling K = %lf\n", K_);
+    fprintf(fptr_, "# Temperature T = %lf\n", -1 / K_);
+    fprintf(fptr_, "# Number of lattice sites = %i\n", N * N);
+    fprintf(fptr_, "# Lattice spacing = %i\n", pLattice->a_);
+    fprintf(fptr_, "# Using %i parallel processes\n", R);
+    fprintf(fptr_, "# %s, %s, %s, %s, %s, %s, %s\n", "Iteration", "Avg E/spin", "Stddev E/spin", "Heat Capacity",
+            "Avg |M|/spin", "Stddev |M|/spin", "Susceptibility");
+    std::vector<std::int64_t> S((size_t)R * 4);
+    int done = 0;
     for (int n = 1; n <= n_samples_eq; ++n) {
-        sample_new_configuration(pLattice);
-        if (write_iter(n) && rank_ == 0) {
-            const double E = calc_energy(pLattice), M = std::fabs(calc_magnetization(pLattice));
-            const double E_avg = E / n_processes_, M_avg = M / n_processes_;
-            const double E2_avg = E * E / n_processes_, M2_avg = M * M / n_processes_;
-            double E_sigma = E2_avg - E_avg * E_avg, M_sigma = M2_avg - M_avg * M_avg;
-            const double C = E_sigma * K_ * K_, Chi = -M_sigma * K_;
-            E_sigma = std::sqrt(E_sigma);
-            M_sigma = std::sqrt(M_sigma);
-            fprintf(fptr_, "%i, %10.7e, %10.7e, %10.7e, %10.7e, %10.7e, %10.7e\n", n, E_avg / pLattice->n_spins_,
-                    E_sigma / pLattice->n_spins_, C, M_avg / pLattice->n_spins_, M_sigma / pLattice->n_spins_, Chi);
+        if (!write_iter(n) && n != n_samples_eq) continue;
+        ck(mcrg_sweep(batch.ctx, (n - done) * spu), "mcrg_sweep");
+        done = n;
+        if (!write_iter(n)) break;
+        ck(mcrg_measure(batch.ctx, 0, S.data(), nullptr), "mcrg_measure");
+        double E_avg = 0, M_avg = 0, E2_avg = 0, M2_avg = 0;
+        for (int r = 0; r < R; ++r) {
+            const double E = K_ * (double)S[(size_t)r * 4 + 0] / ((double)N * N);                 // calc_energy, ising.cpp:158-173
+            const long long sum = (long long)S[(size_t)r * 4 + 3];
+            const double M = compat ? std::fabs((double)((int)sum / (N * N)))                   // ising.cpp:178: integer division
+                                    : std::fabs((double)sum) / ((double)N * N);
+            E_avg += E; M_avg += M; E2_avg += E * E; M2_avg += M * M;
         }
+        E_avg /= R; M_avg /= R; E2_avg /= R; M2_avg /= R;                                       // ising.cpp:57-60
+        double E_sigma = E2_avg - E_avg * E_avg, M_sigma = M2_avg - M_avg * M_avg;
+        const double C = E_sigma * K_ * K_, Chi = -M_sigma * K_;
+        E_sigma = std::sqrt(std::max(0.0, E_sigma));
+        M_sigma = std::sqrt(std::max(0.0, M_sigma));
+        const double per = compat ? (double)pLattice->n_spins_ : 1.0;                          // ising.cpp:72 divides again
+        fprintf(fptr_, "%i, %10.7e, %10.7e, %10.7e, %10.7e, %10.7e, %10.7e\n", n, E_avg / per, E_sigma / per, C, M_avg / per,
+                M_sigma / per, Chi);
     }
-    if (rank_ == 0) {
-        pLattice->write_spins(fptr_);
-        fclose(fptr_);
-        fptr_ = NULL;
-    }
+    ck(mcrg_get_spins_i32_colmajor(batch.ctx, 0, 1, pLattice->spins_.data()), "mcrg_get_spins_i32_colmajor");
+    pLattice->write_spins(fptr_);
+    fclose(fptr_);
+    fptr_ = NULL;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -530,21 +561,52 @@ double MonteCarloRenormalizationGroup::approx_critical_point(int n_samples_eq, i
     if (!settings().quiet) printf("Sampling %i configurations each...\n", n_samples);
     ck(mcrg_run(big.ctx, per_replica, spu, nT, 0), "mcrg_run");                       // levels 0..nT of L
     ck(mcrg_run(small.ctx, per_replica, spu, nT > 0 ? nT - 1 : 0, 0), "mcrg_run");    // levels 0..nT-1 of L/b
-    const std::vector<long double> vL = mcrg_b200::fetch_totals(big).v, vS = mcrg_b200::fetch_totals(small).v;
-    const long double n = vL[lay.slot_n];
-
-    const long double SL_avg = vL[lay.slot_s + 0] / n, SS_avg = vS[lay.slot_s + 0] / n;
+    const mcrg_b200::Totals tL = mcrg_b200::fetch_totals(big), tS = mcrg_b200::fetch_totals(small);
+    // dK per blocking level from the totals of the two batches (mcrg.cpp:283-298)
+    auto estimate = [&](const std::vector<long double> &vL, const std::vector<long double> &vS) {
+        const long double n = vL[lay.slot_n];
+        const long double SL_avg = vL[lay.slot_s + 0] / n, SS_avg = vS[lay.slot_s + 0] / n;
+        std::vector<double> dK(nT);
+        for (int k = 0; k < nT; ++k) {
+            // SLb(k): NN sum of L blocked k+1 times; SSb(k): NN sum of L/b blocked k times (mcrg.cpp:253-263)
+            const long double SLb = vL[lay.slot_s + (k + 1) * MCRG_NOP + 0] / n;
+            const long double SSb = vS[lay.slot_s + k * MCRG_NOP + 0] / n;
+            const long double SLb_SL = vL[lay.slot_sb0 + k * 9 + 0] / n;
+            const long double SSb_SS = (k == 0 ? vS[lay.slot_ss + 0] : vS[lay.slot_sb0 + (k - 1) * 9 + 0]) / n;
+            const long double dSL_dK = SLb_SL - SLb * SL_avg;  // mcrg.cpp:295
+            const long double dSS_dK = SSb_SS - SSb * SS_avg;  // mcrg.cpp:296
+            dK[k] = (double)((SLb - SSb) / (dSL_dK - dSS_dK));
+        }
+        return dK;
+    };
+    const std::vector<double> dK = estimate(tL.v, tS.v);
+    // jackknife over groups of chains (chain r of the large batch and chain r of the small one leave together)
+    kc_errors_.assign(nT, NAN);
+    if (R >= 8) {
+        const int groups = std::min(R, 32);
+        std::vector<std::vector<double>> loo;
+        for (int g = 0; g < groups; ++g) {
+            std::vector<long double> vL = tL.v, vS = tS.v;
+            for (int r = g; r < R; r += groups)
+                for (size_t s = 0; s < vL.size(); ++s) {
+                    vL[s] -= tL.per_replica[r][s];
+                    vS[s] -= tS.per_replica[r][s];
+                }
+            loo.push_back(estimate(vL, vS));
+        }
+        for (int k = 0; k < nT; ++k) {
+            double mean = 0, var = 0;
+            for (auto &l : loo) mean += l[k];
+            mean /= groups;
+            for (auto &l : loo) var += (l[k] - mean) * (l[k] - mean);
+            kc_errors_[k] = std::sqrt(var * (groups - 1) / groups);
+        }
+    }
+    kcs_.assign(nT, NAN);
     double Kc = 0;
     for (int k = 0; k < nT; ++k) {
-        // SLb(k): NN sum of L blocked k+1 times; SSb(k): NN sum of L/b blocked k times (mcrg.cpp:253-263)
-        const long double SLb = vL[lay.slot_s + (k + 1) * MCRG_NOP + 0] / n;
-        const long double SSb = vS[lay.slot_s + k * MCRG_NOP + 0] / n;
-        const long double SLb_SL = vL[lay.slot_sb0 + k * 9 + 0] / n;
-        const long double SSb_SS = (k == 0 ? vS[lay.slot_ss + 0] : vS[lay.slot_sb0 + (k - 1) * 9 + 0]) / n;
-        const long double dSL_dK = SLb_SL - SLb * SL_avg;  // mcrg.cpp:295
-        const long double dSS_dK = SSb_SS - SSb * SS_avg;  // mcrg.cpp:296
-        const long double dK = (SLb - SSb) / (dSL_dK - dSS_dK);
-        Kc = K + (double)dK;
+        Kc = K + dK[k];
+        kcs_[k] = Kc;
         if (!settings().quiet) printf("n = %i: Kc = %lf\n", k, Kc);
         fprintf(fptr_, "%25i, %25i, %25.10lf, %25.10lf\n", iter_, k, K, Kc);
         fflush(fptr_);
@@ -558,11 +620,14 @@ std::shared_ptr<Lattice> MonteCarloRenormalizationGroup::block_spin_transformati
     auto b = pLattice->device_batch();
     static std::atomic<std::uint64_t> calls{0};
     ck(mcrg_set_spins_i32_colmajor(b->ctx, 0, 1, pLattice->spins_.data()), "mcrg_set_spins_i32_colmajor");
-    ck(mcrg_set_sweep_counter(b->ctx, (1ull << 40) + calls.fetch_add(1)), "mcrg_set_sweep_counter");
+    std::uint64_t t_saved = 0;  // the tie coins are keyed by the counter: use a private range, then put the lattice's own
+    ck(mcrg_get_sweep_counter(b->ctx, &t_saved), "mcrg_get_sweep_counter");  // counter back so that its updates never reuse
+    ck(mcrg_set_sweep_counter(b->ctx, (1ull << 40) + calls.fetch_add(1)), "mcrg_set_sweep_counter");  // Metropolis draws
     ck(mcrg_measure(b->ctx, 1, nullptr, nullptr), "mcrg_measure");
     const int Nb = pLattice->N_ / b_;
     imat block_spins(Nb, Nb);
     ck(mcrg_get_level_spins_i32_colmajor(b->ctx, 0, 1, block_spins.data()), "mcrg_get_level_spins_i32_colmajor");
+    ck(mcrg_set_sweep_counter(b->ctx, t_saved), "mcrg_set_sweep_counter");
     return std::shared_ptr<Lattice>(new Lattice(pLattice->a_ * b_, block_spins));
 }
 

@@ -188,6 +188,37 @@ int ref_critical_exponent(const char *workdir, int n_eq, int n_samples, int N, d
     return n_found;
 }
 
+// The real locate_critical_point (mcrg.cpp:146-310, two-lattice matching with the NN operator).  It writes
+// critical_point_L_<L>_K_<K0>.txt into the CWD; the caller passes a scratch directory.  Parses the rows
+// "iteration, level, starting K, approximate Kc" back into out[(iteration-1)*n_levels + level] = Kc; returns the rows found.
+int ref_locate_critical_point(const char *workdir, int n_iterations, int n_eq, int n_samples, int L, double K0, double *out,
+                              int max_rows, double *K_final) {
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) return -1;
+    if (chdir(workdir) != 0) return -2;
+    {
+        QuietStdout q;
+        MonteCarloRenormalizationGroup rg(2);
+        const double K = rg.locate_critical_point(n_iterations, n_eq, n_samples, L, K0);
+        if (K_final) *K_final = K;
+    }
+    std::string filename = "critical_point_L_" + std::to_string(L) + "_K_" + get_rounded_str(K0, 7) + ".txt";
+    FILE *f = fopen(filename.c_str(), "r");
+    int n_found = 0;
+    if (f) {
+        char line[512];
+        while (fgets(line, sizeof line, f)) {
+            if (line[0] == '#') continue;
+            int it, lv;
+            double Ks, Kc;
+            if (sscanf(line, " %d , %d , %lf , %lf", &it, &lv, &Ks, &Kc) == 4 && n_found < max_rows) out[n_found++] = Kc;
+        }
+        fclose(f);
+    }
+    if (chdir(cwd) != 0) return -3;
+    return n_found;
+}
+
 // The sample loop of calc_critical_exponent (mcrg.cpp:42-98) with the per-sample S matrix logged.
 // Same construction order and rng consumption as the reference, so with the same seed it visits the same
 // configurations as ref_critical_exponent.  S_log receives n_samples*(n_lv+1)*2 doubles

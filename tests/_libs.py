@@ -103,6 +103,8 @@ def ref():
         r.ref_write_iter.restype = C.c_int
         r.ref_critical_exponent.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, f64p, f64p, C.c_int]
         r.ref_critical_exponent.restype = C.c_int
+        r.ref_locate_critical_point.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, f64p, C.c_int, C.POINTER(C.c_double)]
+        r.ref_locate_critical_point.restype = C.c_int
         r.ref_mcrg_loop.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         r.ref_mcrg_loop.restype = C.c_double
         r.ref_thermo_series.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, f64p]
@@ -116,6 +118,18 @@ def ref():
 # ---------------------------------------------------------------------------------------------------------
 # lattice generators shared by the parity tests (reference layout: int32 +-1, column-major => arr[j, i])
 # ---------------------------------------------------------------------------------------------------------
+
+def ref_write_iter_py(i):
+    """definitions.cpp:44-68 restated: every iteration below 10, every 10^k below 10^(k+1), then every 10^5."""
+    step = 1
+    bound = 10
+    while bound <= 100000:
+        if i < bound:
+            return i % step == 0
+        step = bound
+        bound *= 10
+    return i % 100000 == 0
+
 
 def random_lattice(N, seed, p_up=0.5):
     rng = np.random.default_rng(seed)

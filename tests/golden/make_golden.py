@@ -153,12 +153,51 @@ def train_log_rows():
     print("train_logs_cycle0.json:", len(rows), "rows")
 
 
+def _kc_worker(args):
+    L, K0, seed, n_iter, n_eq, n_samples = args
+    r = _libs.ref()
+    out = np.zeros(256)
+    kf = C.c_double(0)
+    with tempfile.TemporaryDirectory() as d:
+        r.ref_seed(seed)
+        n = r.ref_locate_critical_point(d.encode(), n_iter, n_eq, n_samples, L, K0, out, 256, C.byref(kf))
+    return out[:n].tolist()
+
+
+def critical_point(procs=6):
+    """The reference's own locate_critical_point (mcrg.cpp:146-310) over independent seeds: K after ONE iteration from
+    displaced starting points (per blocking level: the response of the two-lattice estimator, sign and size), and the
+    iterated fixed point.  Mean and standard error over seeds -> tests/golden/critical_point.json."""
+    res = {"note": "reference locate_critical_point, Wolff sampler, hot start; rows are [iteration][level] Kc; mean and "
+                   "standard error over independent seeds of the global rng", "runs": []}
+    n_seeds = 16
+    plan = [(16, -0.43, 1, 2000, 1000000), (16, -0.45, 1, 2000, 1000000), (16, -0.44, 3, 2000, 1000000),
+            (32, -0.43, 1, 2000, 600000), (32, -0.45, 1, 2000, 600000), (32, -0.44, 3, 2000, 600000),
+            (64, -0.4405, 2, 3000, 200000)]
+    with mp.Pool(procs) as pool:
+        for L, K0, n_iter, n_eq, n_samples in plan:
+            rows = np.array(pool.map(_kc_worker, [(L, K0, 31000 + 17 * s + L, n_iter, n_eq, n_samples) for s in range(n_seeds)], chunksize=1))
+            n_lv = rows.shape[1] // n_iter
+            rows = rows.reshape(n_seeds, n_iter, n_lv)
+            res["runs"].append(dict(L=L, K0=K0, n_iterations=n_iter, n_eq=n_eq, n_samples=n_samples, n_seeds=n_seeds,
+                                    mean=rows.mean(0).tolist(), err=(rows.std(0, ddof=1) / np.sqrt(n_seeds)).tolist(),
+                                    sd_single_run=rows.std(0, ddof=1).tolist()))
+            print("kc", L, K0, rows.mean(0)[-1], rows.std(0, ddof=1)[-1] / np.sqrt(n_seeds), flush=True)
+            with open(os.path.join(HERE, "critical_point.json"), "w") as f:
+                json.dump(res, f, indent=1)
+    print("critical_point.json written")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--fast", action="store_true")
+    ap.add_argument("--kc", action="store_true", help="only the critical-point fixtures (about an hour on 6 cores)")
     a = ap.parse_args()
     if not _libs.ref_available():
         sys.exit("oracle/_ref/libmcrg_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+    if a.kc:
+        critical_point()
+        sys.exit(0)
     deterministic()
     train_log_rows()
     if not a.fast:

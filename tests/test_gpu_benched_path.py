@@ -32,6 +32,7 @@ CASES = [
     (2048, [KC, -0.4497, -0.4688], 33, 16, 1, -1, 0),
     (4096, [KC, -0.4320459], 17, 0, 1, -1, 0),         # the headline shape: one graph + 1 sample
     (512, [KC, -0.42], 34, 18, 1, -1, 32),             # forced strips below the resident limit (one k_tail-only pyramid)
+    (1024, [KC, -0.45], 18, 16, 1, -1, 44),            # strips that do not divide L, unaligned to the tie-coin chunks
 ]
 
 

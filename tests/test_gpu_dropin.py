@@ -45,7 +45,7 @@ def test_calc_critical_exponent_matches_reference_driver(tmp_path):
     with open(os.path.join(_libs.ROOT, "tests", "golden", "statistical.json")) as f:
         ref = next(t for t in json.load(f)["lambda"] if t["N"] == 32)
     out = run([APP, "exponent", "32", repr(KC), "500", "2000000"], tmp_path,
-              {"MCRG_REPLICAS": "1024", "MCRG_SWEEPS_PER_UPDATE": "16", "MCRG_SEED": "4711"})
+              {"MCRG_REPLICAS": "1024", "MCRG_UPDATE": "metropolis", "MCRG_SWEEPS_PER_UPDATE": "16", "MCRG_SEED": "4711"})
     # console and file formats of mcrg.cpp:12-17, 31-39, 133-141
     assert "==========  RENORMALIZATION GROUP  ==========" in out and "* Scaling factor b = 2" in out
     assert re.search(r"n = 0: lambda = \d\.\d{6}, nu = \d\.\d{6}", out)
@@ -93,14 +93,89 @@ def test_locate_critical_point(tmp_path):
 
 @pytest.mark.skipif(not os.path.exists(REF_MAIN), reason="ref_main is built only where /root/reference exists")
 def test_reference_main_cpp_runs_unchanged(tmp_path):
-    """main.cpp:8-17: b=2, N=128, 1e4 equilibration updates, 1e6 samples, at K=-0.44 and at K_c."""
-    out = run([REF_MAIN], tmp_path, {"MCRG_REPLICAS": "4096", "MCRG_SWEEPS_PER_UPDATE": "2"}, timeout=900)
+    """main.cpp:8-17: b=2, N=128, 1e4 equilibration updates, 1e6 samples, at K=-0.44 and at K_c, with the drop-in's defaults:
+    at N = 128 those are cluster updates (the reference's update family), one per sample as in mcrg.cpp:75, so the 1e4
+    equilibration updates equilibrate and the chains decorrelate like the reference's.  lambda per level must sit where the
+    2D Ising RG puts it: 1.95 at the first level (the compiled reference gives 1.951 +- 0.003 at N = 64,
+    tests/golden/statistical.json), 2.0 on the inner levels, 2.02 on the last one (the 2 x 2 lattice)."""
+    out = run([REF_MAIN], tmp_path, {"MCRG_REPLICAS": "4096"}, timeout=900)
     assert out.count("* Critical exponent: nu =") == 2
     for name in ("critical_exponent_N_128_K_-0.44.txt", f"critical_exponent_N_128_K_{KC:.7g}.txt"):
         rows = [l for l in (tmp_path / name).read_text().splitlines() if not l.startswith("#")]
         assert len(rows) == 6  # floor(log 128 / log 2) - 1 blocking levels
         lam = [float(r.split(",")[1]) for r in rows]
-        assert all(1.7 < x < 2.3 for x in lam), lam
+        assert 1.93 < lam[0] < 1.97, lam
+        assert all(1.97 < x < 2.02 for x in lam[1:5]), lam
+        assert 1.99 < lam[5] < 2.06, lam
+
+
+def test_equilibrate_log_is_averaged_over_chains(tmp_path):
+    """IsingModel::equilibrate(write=true), ising.cpp:22-74: the log averages E, |M|, E^2, M^2 over the ranks; here over
+    MCRG_REPLICAS device chains.  File name, header and row format are the reference's; rows appear at its write_iter
+    schedule; sigma_E, C, chi are non-zero; E converges to the reference sampler's equilibrium value; MCRG_COMPAT=1
+    (default) reproduces the reference's integer-division magnetisation and second division by n_spins."""
+    with open(os.path.join(_libs.ROOT, "tests", "golden", "statistical.json")) as f:
+        ref = next(t for t in json.load(f)["thermo"] if t["N"] == 32 and abs(t["K"] - KC) < 1e-9)
+    N, n_eq, R = 32, 2000, 2048
+    logs = {}
+    for compat in ("1", "0"):
+        d = tmp_path / f"compat{compat}"
+        d.mkdir()
+        run([APP, "equilibrate", str(N), repr(KC), str(n_eq)], d,
+            {"MCRG_REPLICAS": str(R), "MCRG_SEED": "31", "MCRG_COMPAT": compat, "MCRG_QUIET": "1"})
+        fn = d / f"equilibrate_N_{N}_K_{KC:.7g}.txt"
+        assert fn.exists(), os.listdir(d)
+        logs[compat] = fn.read_text().splitlines()
+    for compat, lines in logs.items():
+        assert lines[0] == f"# Nearest neighbor coupling K = {KC:.6f}" and lines[1] == f"# Temperature T = {-1 / KC:.6f}"
+        assert lines[2] == f"# Number of lattice sites = {N * N}" and lines[3] == "# Lattice spacing = 1"
+        assert lines[4] == f"# Using {R} parallel processes"
+        assert lines[5] == "# Iteration, Avg E/spin, Stddev E/spin, Heat Capacity, Avg |M|/spin, Stddev |M|/spin, Susceptibility"
+        rows = [l for l in lines[6:] if l and not l.startswith("#")]
+        iters = [int(r.split(",")[0]) for r in rows]
+        assert iters == [n for n in range(1, n_eq + 1) if _libs.ref_write_iter_py(n)]
+        assert all(re.fullmatch(r"\d+(, -?\d\.\d{7}e[+-]\d\d){6}", r) for r in rows), rows[:2]
+        spins = [l for l in lines if l.startswith("# ") and l.rstrip().endswith(",")]
+        assert len(spins) == N and all(len(l[2:].split(",")) == N + 1 for l in spins)  # write_spins, lattice.cpp:58-70
+    # np.genfromtxt-style parse (comment lines skipped), as the reference's plotting scripts read such tables
+    fixed = np.genfromtxt(logs["0"], delimiter=",", comments="#")
+    compat = np.genfromtxt(logs["1"], delimiter=",", comments="#")
+    assert fixed.shape == compat.shape and fixed.shape[1] == 7
+    last = fixed[-1]
+    assert last[2] > 0 and last[3] > 0 and last[5] > 0 and last[6] > 0  # sigma_E, C, sigma_M, chi: averages over > 1 chain
+    e_ref, e_err = 4 * KC * ref["bond"][0], 4 * abs(KC) * ref["bond"][1]
+    assert abs(last[1] - e_ref) < 4 * np.hypot(e_err, last[2] / np.sqrt(R)), (last[1], e_ref)
+    assert abs(last[4] - ref["absm"][0]) < 4 * np.hypot(ref["absm"][1], last[5] / np.sqrt(R)), (last[4], ref["absm"])
+    # same seed => same chains: the compat log is the same energy divided by n_spins once more (ising.cpp:72), and its
+    # magnetisation column is the integer division of ising.cpp:178 (0 unless a chain is fully ordered)
+    assert np.allclose(compat[:, 1] * N * N, fixed[:, 1], rtol=2e-7)
+    assert (compat[:, 4] == 0).all()
+
+
+def test_test_scalar_output_file(tmp_path):
+    """RenormalizationGroupNeuralNetwork::test_scalar_output, rgnn.cpp:192-278: 101 couplings K0 - DeltaK .. K0 + DeltaK in steps
+    of DeltaK / 50, one row "K T <u_L> Var <u_S> Var mse" each in the reference's format; at K0 the row agrees with the
+    cycle-0 row of the reference's own training log at that coupling (same W0, same observable)."""
+    with open(os.path.join(_libs.ROOT, "tests", "golden", "train_logs_cycle0.json")) as f:
+        row = next(r for r in json.load(f) if abs(r["K"] - (-0.4406868)) < 1e-9)
+    K0, DK = -0.4406868, 0.02
+    out = run([APP, "test", "8", repr(K0), repr(DK), "400000", "500"], tmp_path, {"MCRG_REPLICAS": "2048", "MCRG_SWEEPS_PER_UPDATE": "4", "MCRG_QUIET": "1"})
+    assert "RESULT done" in out
+    lines = (tmp_path / f"test_scalar_b2_L8_K{K0:.7g}.txt").read_text().splitlines()
+    assert lines[0] == "" and lines[1] == "# Coupling K, Temperature T, Avg Output L, Var Output L, Avg Output S, Var Output S, MSE"
+    rows = lines[2:]
+    assert len(rows) in (100, 101)  # the reference's floating-point loop bound (K <= K0 + DeltaK after 100 additions)
+    assert all(re.fullmatch(r"(\s*-?\d\.\d{7}e[+-]\d\d){7}", r) for r in rows)
+    t = np.array([[float(x) for x in r.split()] for r in rows])
+    assert np.allclose(t[:, 1], -1.0 / t[:, 0], rtol=1e-6) and np.allclose(np.diff(t[:, 0]), DK / 50, rtol=1e-4)
+    assert np.allclose(t[:, 6], (t[:, 2] - t[:, 4]) ** 2, rtol=1e-4, atol=1e-12)
+    mid = t[50]
+    assert abs(mid[0] - K0) < 1e-9
+    n_eff = 400000 / 4  # generous: Metropolis at L = 8 with 4 sweeps per sample
+    assert abs(mid[2] - row["uL"]) < 3 * np.hypot(1.5 * np.sqrt(row["varL"] / row["n_samples"]), np.sqrt(mid[3] / n_eff)), (mid, row)
+    assert abs(mid[4] - row["uS"]) < 3 * np.hypot(1.5 * np.sqrt(row["varS"] / row["n_samples"]), np.sqrt(mid[5] / n_eff)), (mid, row)
+    # the output moves monotonically with the coupling across the window (it measures disorder inside the 2 x 2 blocks)
+    assert abs(np.corrcoef(t[:, 0], t[:, 2])[0, 1]) > 0.9
 
 
 def test_rgnn_cycle0_matches_reference_training_logs(tmp_path):

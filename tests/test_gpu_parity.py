@@ -81,6 +81,21 @@ def test_packed_and_pipelined_uploads_roundtrip(mc, L, R):
         ctx.set_spins_commit()
         ctx.sync()
         assert np.array_equal(ctx.get_spins(0, R), spins)
+        # one upload of each kind in flight at once (the hybrid e2e path of bench.py): replica 0 as int32 through the copy
+        # engine, replicas 1.. host-packed; one commit takes in both; a second begin of the same kind is refused
+        if R >= 2:
+            ctx.init_cold()
+            rest = np.zeros(mc.capi.packed_words(L, R - 1), np.uint32)
+            mc.capi.host_pack(spins[1:].ctypes.data, L, R - 1, rest.ctypes.data, 1)
+            pk_rest = torch.from_numpy(rest.view(np.int32).copy()).pin_memory()
+            ctx.set_spins_begin(pinned.data_ptr(), 1, first=0)
+            ctx.set_spins_packed_begin(pk_rest.data_ptr(), R - 1, first=1)
+            with pytest.raises(mc.capi.McrgError):
+                ctx.set_spins_begin(pinned.data_ptr(), 1, first=0)
+            ctx.sweep(1)
+            ctx.set_spins_commit()
+            ctx.sync()
+            assert np.array_equal(ctx.get_spins(0, R), spins)
 
 
 @pytest.mark.parametrize("L", [2, 4, 8, 32, 64, 128, 512])
@@ -145,8 +160,10 @@ def test_observables_match_oracle(mc, L):
 
 
 @pytest.mark.parametrize("L,strip", [(4, 0), (8, 2), (16, 0), (32, 8), (64, 0), (128, 16), (256, 0), (512, 0), (1024, 0),
-                                     (2048, 32)])
+                                     (2048, 32), (64, 6), (128, 10), (512, 20), (1024, 44), (2048, 18), (2048, 6)])
 def test_pyramid_matches_oracle(mc, L, strip):
+    """strip = 0: the library's own choice; otherwise forced strips, including heights that do not divide L (ragged last
+    strip) and that are not aligned to the tie-coin chunks of the measurement loop."""
     seed, base, t = 4242, 9, (1 << 34) + 17
     cases = lattice_cases(L)
     if L >= 1024:
@@ -227,7 +244,8 @@ def test_tie_coins_are_fair_and_keyed(mc):
 
 @pytest.mark.parametrize("L,strip,fuse,n_sweeps", [(2, 0, 1, 5), (2, 2, 2, 4), (4, 0, 1, 3), (8, 2, 1, 4), (16, 0, 2, 5), (32, 8, 1, 3), (64, 0, 1, 4),
                                                    (64, 16, 3, 7), (128, 0, 2, 3), (256, 32, 1, 2), (512, 0, 1, 2),
-                                                   (1024, 16, 2, 2), (2048, 0, 1, 2), (2048, 4, 2, 2)])
+                                                   (1024, 16, 2, 2), (2048, 0, 1, 2), (2048, 4, 2, 2), (64, 6, 1, 3), (256, 10, 2, 3),
+                                                   (1024, 36, 1, 2), (2048, 22, 1, 2)])
 def test_sweeps_match_scalar_metropolis(mc, L, strip, fuse, n_sweeps):
     o = _libs.oracle()
     seed, base, t0 = 0xABCDEF0123, 3, (1 << 32) - 2  # crosses the 32-bit boundary of the sweep counter
@@ -281,7 +299,7 @@ def test_sweep_is_independent_of_strip_geometry_at_full_size(mc):
     result cannot depend on the strip height or on how many sweeps are fused per launch (halo recomputation with
     counter-based random numbers), plus one exact oracle sweep at 4096."""
     o = _libs.oracle()
-    for L, variants in ((4096, [(0, 1), (8, 1), (64, 2), (16, 3)]), (16384, [(0, 1), (8, 2), (32, 1)])):
+    for L, variants in ((4096, [(0, 1), (8, 1), (64, 2), (16, 3), (14, 1), (44, 1)]), (16384, [(0, 1), (8, 2), (32, 1), (20, 1)])):
         results = []
         for strip, fuse in variants:
             with mc.Context(L, 1, seed=99) as ctx:
@@ -357,7 +375,7 @@ def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start, update="me
     hi1 = np.zeros(n_lv * 9, np.int64); lo1 = np.zeros(n_lv * 9, np.uint64)
     hi2 = np.zeros(n_lv * 9, np.int64); lo2 = np.zeros(n_lv * 9, np.uint64)
     absM = M2 = 0
-    M4 = 0.0
+    M4 = 0
     t = t0
     for _ in range(n_samples):
         S4 = _libs.pyramid(L, s, seed, replica, t, max_levels)
@@ -370,7 +388,7 @@ def cpu_run(L, seed, replica, K, t0, n_samples, m, max_levels, start, update="me
                     if lv >= 1:
                         SB0[lv - 1][b * 3 + a] += int(S3[lv, a]) * int(S3[0, b])
         M = int(S4[0, 3])
-        absM += abs(M); M2 += M * M; M4 += float(M) ** 4
+        absM += abs(M); M2 += M * M; M4 += M ** 4
         (o.orc_swendsen_wang if update == "cluster" else o.orc_metropolis)(L, s, K, seed, replica, t, m)
         t += m
     SbS = [int(h) * (1 << 64) + int(l) for h, l in zip(hi1, lo1)]
@@ -384,7 +402,8 @@ def assert_accumulators(mc, a, ad, want, tag=None):
     n_lv = want["n_lv"]
     assert a[lay.slot_n] == want["n"], tag
     assert a[lay.slot_absm] == want["absM"] and a[lay.slot_m2] == want["M2"], tag
-    assert abs(ad[lay.dslot_m4] - want["M4"]) <= 1e-12 * max(1.0, want["M4"]), tag
+    assert lay.m4(a) == want["M4"], tag  # exact: three 128-bit slots (include/mcrg_b200.h: slot_m4)
+    assert abs(ad[lay.dslot_m4] - float(want["M4"])) <= 1e-12 * max(1.0, float(want["M4"])), tag
     for lv in range(n_lv + 1):
         for op in range(3):
             assert a[lay.slot_s + lv * 3 + op] == int(want["S"][lv * 3 + op]), (tag, lv, op)
@@ -462,6 +481,7 @@ def test_products_beyond_int64(mc):
     assert a[lay.slot_ss + 0] == n * s0 * s0 and n * s0 * s0 > 2**63
     assert a[lay.slot_sbs + 0] == n * s1 * s0
     assert a[lay.slot_m2] == n * (L * L) ** 2
+    assert lay.m4(a) == n * (L * L) ** 4 and n * (L * L) ** 4 > 2**117  # sum M^4: exact in its three slots
 
 
 # ---------------------------------------------------------------------------------------------------------

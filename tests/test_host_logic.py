@@ -44,7 +44,7 @@ def test_library_is_sm100a_and_has_no_cpu_fallback(mc):
     with pytest.raises(mc.McrgError):
         mc.Context(64, 1)
     lay = mc.capi.acc_layout()
-    assert lay.n_slots == 3 + 3 * 16 + 9 * 16 + 9 * 15 + 9 * 15
+    assert lay.n_slots == 3 + 3 * 16 + 9 * 16 + 9 * 15 + 9 * 15 + 3 and lay.slot_m4 == lay.n_slots - 3  # + the three exact parts of sum M^4
     assert mc.capi.levels_full(128) == 6 and mc.capi.levels_full(4096) == 11 and mc.capi.levels_full(16384) == 13
 
 

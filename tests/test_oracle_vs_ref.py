@@ -180,3 +180,10 @@ def test_rgnn_forward_and_gradient():
                 o.orc_rgnn_gradient(N, s, 2, W.copy(), 1e-4, ga)
                 r.ref_rgnn_gradient(N, s, 2, W, 1e-4, gb)
                 assert np.allclose(ga, gb, rtol=0, atol=1e-7 * max(1.0, np.abs(gb).max()))
+
+
+def test_write_iter_restatement_matches_reference():
+    """definitions.cpp:44-68 (the log-spaced output schedule of equilibrate(write=true)) against tests/_libs.ref_write_iter_py."""
+    r = _libs.ref()
+    for i in list(range(1, 3000)) + list(range(9990, 10011)) + [99999, 100000, 100001, 150000, 200000, 1000000, 1234567]:
+        assert bool(r.ref_write_iter(i)) == _libs.ref_write_iter_py(i), i
