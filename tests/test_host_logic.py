@@ -163,7 +163,7 @@ def test_shard_replicas(mc):
 
 
 def test_bench_reference_arm_runs_on_cpu():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--L", "128", "--steps", "2",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C2", "--ref-samples", "50", "--steps", "2",
                           "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
