@@ -86,77 +86,43 @@ MCRG_HD uint32_t shift_down_index(uint32_t cur, uint32_t prev, int bits, uint32_
 
 MCRG_HD uint32_t valid_mask(int bits) { return bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u); }
 
-// ---- checkerboard Metropolis on words of 32 same-colour sites ----------------------------------------------------
+// ---- checkerboard Metropolis on one word of 32 same-colour sites --------------------------------------------
 // t: the sites; u, d, s0, s1: their four neighbours (other colour).  `anti` = 0 for K <= 0 (ferromagnetic,
 // ising.cpp:8-9 sign convention), ~0 for K > 0.  A = number of bonds the flip would repair; flip always if
-// A >= 2, with probability exp(-4|K|) if A == 1 and exp(-8|K|) if A == 0, decided as U < T4 / U < T8 with a 32-bit
-// uniform U per site whose k-th most significant bit is bit `lane` of a Philox output word ("bit plane" k = call k>>2,
-// element k&3).  The comparison is evaluated lazily, MSB first, for all 32 lanes at once, and stops as soon as every lane
-// is decided — identical to the full 32-bit comparison in the oracle.
-//
-// Which call supplies the planes (the sampler specification, scalar form: oracle/mcrg_oracle.c orc_metropolis):
-// the rows of a colour are taken in PAIRS (A, B = A + 1 mod L), A being the row with (y + colour) odd.
-//   planes 0-3   call j = 0 of the site's own word;
-//   planes 4-7   call j = 1 of the A row's word — for every lane of the A row, and for those lanes of the B row whose
-//                lane in the A row was ALREADY DECIDED after planes 0-3 (it did not need a random number at all, or its
-//                first four bits settled the comparison), so that no random bit is ever read by two sites; the other
-//                lanes of the B row take call j = 1 of the B row's own word;
-//   planes 8-31  calls j = 2.. of the site's own word.
-// After four planes a lane is undecided with probability 1/16, so the A row's second call serves ~2 lanes and almost all
-// of its bits would be thrown away; sharing it halves the Philox work that pass spends.  Whether a B lane reads the shared
-// or its own call depends only on the A row's state and first four bits, which are independent of the bits in question:
-// every site still sees 32 independent uniform bits, the update is the same Metropolis update.
+// A >= 2, with probability exp(-4|K|) if A == 1 and exp(-8|K|) if A == 0, decided as U < T4 / U < T8 where
+// the 32-bit uniform U of lane l has, as its k-th most significant bit, bit l of the k-th Philox output word
+// (call j = k>>2, element k&3).  The comparison is evaluated lazily, MSB first, for all 32 lanes at once,
+// and stops as soon as every lane is decided — identical to the full 32-bit comparison in the oracle.
 struct McParams {
     uint64_t seed;
     uint32_t T4, T8;  // floor(exp(-4|K|) 2^32), floor(exp(-8|K|) 2^32)
     uint32_t anti;    // 0 or 0xFFFFFFFF
 };
 
-// four planes [plane0, plane0 + 4) of the lazy comparison: eq4 / eq8 = lanes still undecided (A == 1 / A == 0)
-MCRG_HD void mc_spec_planes(const U4 &r, int plane0, const McParams &p, uint32_t &eq4, uint32_t &eq8, uint32_t &lt) {
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+MCRG_HD uint32_t metropolis_flip_mask(uint32_t t, uint32_t u, uint32_t d, uint32_t s0, uint32_t s1, uint32_t mask,
+                                      const McParams &p, uint32_t word_id, uint32_t replica, uint64_t sweep) {
+    const uint32_t a1 = t ^ u ^ p.anti, a2 = t ^ d ^ p.anti, a3 = t ^ s0 ^ p.anti, a4 = t ^ s1 ^ p.anti;
+    const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
+    const uint32_t ge2 = c12 | c34 | (x12 & x34);          // A >= 2
+    const uint32_t m1 = (x12 ^ x34) & ~(c12 | c34) & mask; // A == 1
+    const uint32_t m0 = ~(a1 | a2 | a3 | a4) & mask;        // A == 0
+    uint32_t eq4 = m1, eq8 = m0, lt = 0;
+    uint32_t T4s = p.T4, T8s = p.T8;
+    for (int j = 0; j < 8 && (eq4 | eq8) != 0u; ++j) {
+        const U4 r = philox_keyed(p.seed, word_id, replica, sweep, PURPOSE_MC, j);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int k = plane0 + e;
-        const uint32_t tm4 = (uint32_t)(-(int32_t)((p.T4 >> (31 - k)) & 1u));
-        const uint32_t tm8 = (uint32_t)(-(int32_t)((p.T8 >> (31 - k)) & 1u));
-        lt |= (eq4 & ~rr[e] & tm4) | (eq8 & ~rr[e] & tm8);
-        eq4 &= ~(rr[e] ^ tm4);
-        eq8 &= ~(rr[e] ^ tm8);
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t tm4 = (uint32_t)(-(int32_t)(T4s >> 31));
+            const uint32_t tm8 = (uint32_t)(-(int32_t)(T8s >> 31));
+            lt |= (eq4 & ~rr[e] & tm4) | (eq8 & ~rr[e] & tm8);
+            eq4 &= ~(rr[e] ^ tm4);
+            eq8 &= ~(rr[e] ^ tm8);
+            T4s <<= 1;
+            T8s <<= 1;
+        }
     }
-}
-
-// One row pair, one word column: flip masks of the A row's word (id word_a) and the B row's word (id word_b).
-MCRG_HD void metropolis_flip_pair(uint32_t ta, uint32_t ua, uint32_t da, uint32_t s0a, uint32_t s1a, uint32_t tb, uint32_t ub,
-                                  uint32_t db, uint32_t s0b, uint32_t s1b, uint32_t mask, const McParams &p, uint32_t word_a,
-                                  uint32_t word_b, uint32_t replica, uint64_t sweep, uint32_t &flip_a, uint32_t &flip_b) {
-    uint32_t ge2[2], eq4[2], eq8[2], lt[2] = {0u, 0u};
-    const uint32_t tt[2] = {ta, tb}, uu[2] = {ua, ub}, dd[2] = {da, db}, ss0[2] = {s0a, s0b}, ss1[2] = {s1a, s1b};
-    const uint32_t word[2] = {word_a, word_b};
-    for (int r = 0; r < 2; ++r) {
-        const uint32_t a1 = tt[r] ^ uu[r] ^ p.anti, a2 = tt[r] ^ dd[r] ^ p.anti, a3 = tt[r] ^ ss0[r] ^ p.anti, a4 = tt[r] ^ ss1[r] ^ p.anti;
-        const uint32_t x12 = a1 ^ a2, c12 = a1 & a2, x34 = a3 ^ a4, c34 = a3 & a4;
-        ge2[r] = c12 | c34 | (x12 & x34);                   // A >= 2
-        eq4[r] = (x12 ^ x34) & ~(c12 | c34) & mask;         // A == 1
-        eq8[r] = ~(a1 | a2 | a3 | a4) & mask;               // A == 0
-        mc_spec_planes(philox_keyed(p.seed, word[r], replica, sweep, PURPOSE_MC, 0), 0, p, eq4[r], eq8[r], lt[r]);
-    }
-    const uint32_t und_a = eq4[0] | eq8[0];  // lanes of the A row that go on to planes 4-7
-    if ((und_a | eq4[1] | eq8[1]) != 0u) {
-        const U4 shared = philox_keyed(p.seed, word_a, replica, sweep, PURPOSE_MC, 1);
-        mc_spec_planes(shared, 4, p, eq4[0], eq8[0], lt[0]);
-        uint32_t s4 = eq4[1] & ~und_a, s8 = eq8[1] & ~und_a;  // B lanes that read the shared call
-        uint32_t o4 = eq4[1] & und_a, o8 = eq8[1] & und_a;    // B lanes that read their own call
-        mc_spec_planes(shared, 4, p, s4, s8, lt[1]);
-        if ((o4 | o8) != 0u) mc_spec_planes(philox_keyed(p.seed, word_b, replica, sweep, PURPOSE_MC, 1), 4, p, o4, o8, lt[1]);
-        eq4[1] = s4 | o4;
-        eq8[1] = s8 | o8;
-    }
-    for (int r = 0; r < 2; ++r)
-        for (int j = 2; j < 8 && (eq4[r] | eq8[r]) != 0u; ++j)
-            mc_spec_planes(philox_keyed(p.seed, word[r], replica, sweep, PURPOSE_MC, j), 4 * j, p, eq4[r], eq8[r], lt[r]);
-    flip_a = (ge2[0] | lt[0]) & mask;
-    flip_b = (ge2[1] | lt[1]) & mask;
+    return (ge2 | lt) & mask;
 }
 
 // ---- b = 2 majority rule (mcrg.cpp:314-348) on four bit-planes a,b,c,d of the same blocks ----------------------

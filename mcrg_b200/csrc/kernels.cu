@@ -162,35 +162,58 @@ __device__ __forceinline__ void unstage_rows(uint32_t *dst_plane, const uint32_t
 }
 
 // ---- Metropolis update of a strip, device form -----------------------------------------------------------------
-// Same decisions as update_pair0() / metropolis_flip_pair() (the scalar specification is the oracle's orc_metropolis),
-// organised for the SM.  Rows are taken in pairs (A, B) — see bitops.cuh for the pairing rule:
-//   pass 1  every word pair: neighbour counts (full adder), then three Philox calls back to back — call 0 of each word and
-//           call 1 of the A row's word, which the B row shares on the lanes the A row does not need (independent chains ->
-//           ILP; the word-independent part of rounds 0-1 is shared, mc_philox_pair / mc_philox_j) — and 8 lazily-compared bit
-//           planes per word, straight-line, no divergence; the first four planes by code specialised on the leading
-//           threshold bits (mc_compare4_nz).  After 8 planes a lane is still undecided with probability 2^-8, i.e. ~10 % of
-//           the words keep a few undecided lanes, and ~5 % of the B words have a lane that could not share: those words are
-//           appended to the warp's shared-memory queue (ballot rank), decided lanes are written back at once.
-//   pass 2  the queue is consumed densely, one entry per thread (mc_finish): own call 1 for the lanes that could not
-//           share, then calls 2.. until every lane is decided.
-// The per-plane threshold masks (McTable, mcfast.cuh) are a 64-entry table in shared memory.
+// Same decisions as update_word0()/metropolis_flip_mask() in tile.cuh (the scalar specification is the oracle's
+// orc_metropolis), organised for the SM:
+//   pass 1  every word: neighbour count (full adder), then Philox calls j = 0 and 1 back to back (two independent chains ->
+//           ILP; the word-independent part of rounds 0-1 is shared, mc_philox_pair) and 8 lazily-compared bit planes,
+//           straight-line, no divergence; the first four planes by code specialised on the leading threshold bits
+//           (mc_compare4_nz).  After 8 planes a lane is still undecided with probability 2^-8, i.e. ~10 % of the words
+//           keep a few undecided lanes: those words are appended to the warp's shared-memory queue (ballot rank), decided
+//           lanes are written back at once.
+//   pass 2  the queue is consumed densely, one entry per thread, calls j = 2.. until every lane is decided.
+// The per-plane threshold masks (bit k of T4 / T8 replicated over a word) are a 64-entry table in shared memory:
+// broadcast LDS on the otherwise idle LSU pipe instead of shifts on the ALU pipe, which is the binding pipe.
+struct McTable {
+    uint32_t tm[32][2];  // [plane][0: T4 bit, 1: T8 bit] as 0 / 0xFFFFFFFF
+};
+
+__device__ __forceinline__ void mc_compare4(const U4 &r, const McTable *tab, int plane0, uint32_t sel, uint32_t &eq,
+                                            uint32_t &lt) {
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint2 t48 = *reinterpret_cast<const uint2 *>(tab->tm[plane0 + e]);
+        const uint32_t tm = (sel & t48.x) | (~sel & t48.y);  // this lane's threshold bit (A==1 lanes: T4, A==0: T8)
+        lt |= eq & ~rr[e] & tm;                              // U bit 0 where T bit 1, prefix equal: U < T
+        eq &= ~(rr[e] ^ tm);
+    }
+}
+
 struct McQueue {
-    uint4 *ent;      // [warp][cap]: {tile word offset, undecided lanes (call 2 next), selector (A==1 lanes), lanes that start at own call 1}
+    uint4 *ent;      // [warp][cap]: {tile word offset, undecided lanes, selector (A==1 lanes), -}
     int cap;         // entries per warp
 };
 
-// One half-sweep (colour c) over local rows [lr_lo, lr_lo + nrows); lr_lo is an A row and nrows is even.
-// Thread layout: column w = tid & (W-1), row group g = tid >> lw; a group owns a CONTIGUOUS block of row pairs and every
-// thread walks down its column.  The other-colour words above / at / below the current rows then form a sliding window
+// finish one word whose lanes `eq` are still undecided after planes [0, 4*j0): calls j0, j0+1, ... (rare path)
+__device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0, const McTable *tab, const McPhiloxHead &h,
+                                              uint64_t seed, uint32_t word_id, uint32_t c3_base) {
+    uint32_t lt = 0;
+    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox_j(h, seed, word_id, c3_base, j), tab, 4 * j, sel, eq, lt);
+    return lt;
+}
+
+// One half-sweep (colour c) over local rows [lr_lo, lr_lo + nrows).
+// Thread layout: column w = tid & (W-1), row group g = tid >> lw; a group owns a CONTIGUOUS block of rows and every
+// thread walks down its column.  The other-colour words above / at / below the current row then form a sliding window
 // in registers (one new load per row instead of three), all shared-memory addresses are "pointer + constant", and the
 // direction of the in-row neighbour shift — which alternates with the row parity — is a template parameter of the
-// pair body.  For 32-bit words the shift is one funnel shift.
-// Words that still have undecided lanes after pass 1 are appended to a queue PRIVATE TO THE WARP (slot = warp-uniform
-// running count + rank in the ballot: no atomics, no shuffles) and finished densely by the same warp — only __syncwarp()
-// between the passes.  Every warp executes the same number of steps (inactive steps are predicated off), so the ballots are
-// full-warp even when a warp spans several row groups (W < 32).
+// row body (rows are processed in pairs).  For 32-bit words the shift is one funnel shift.
+// Words that still have undecided lanes after the 8 planes of pass 1 are appended to a queue PRIVATE TO THE WARP
+// (slot = warp-uniform running count + rank in the ballot: no atomics, no shuffles) and finished densely by the same
+// warp — only __syncwarp() between the passes.  Every warp executes the same number of row steps (inactive steps are
+// predicated off), so the ballots are full-warp even when a warp spans several row groups (W < 32).
 struct McWalk {
-    uint32_t *pc;        // this thread's word of the A row being updated
+    uint32_t *pc;        // this thread's word of the row being updated
     const uint32_t *po;  // the same position in the other colour's plane
     uint32_t u, n0;      // other-colour words of rows lr-1 and lr
     uint32_t yw;         // (y_first + lr) << lw, NOT wrapped: the word id masks it
@@ -199,7 +222,7 @@ struct McWalk {
 };
 
 struct McConst {
-    uint4 *my_q;         // this warp's queue segment
+    uint4 *my_q;         // this warp's queue segment: {offset, undecided lanes, selector, -}
     const McTable *tab;
     McPhiloxHead head;   // the part of Philox rounds 0 and 1 that is constant over the half-sweep
     uint64_t seed;
@@ -210,71 +233,84 @@ struct McConst {
 
 // word id of the Philox counter: colour*L*W + y*W + w.  wid_c = colour*L*W + w and (yw & yw_mask) = (y mod L)*W occupy
 // disjoint bits, so one LOP3 builds it from the running row counter.
-__device__ __forceinline__ uint32_t mc_word_id(uint32_t yw, const McConst &g) { return (yw & g.yw_mask) | g.wid_c; }
-
-// append one word to the warp's queue (every lane of the warp calls this; `need` = this lane has something to append)
-__device__ __forceinline__ void mc_push(McWalk &k, const McConst &g, bool need, uint32_t off, uint32_t eq, uint32_t sel,
-                                        uint32_t own, uint32_t yw) {
-    const unsigned pend = __ballot_sync(0xFFFFFFFFu, need);
-    if (need) {
-        const int slot = k.n_queued + __popc(pend & g.lanes_below);
-        if (slot < g.qcap) {
-            g.my_q[slot] = make_uint4(off, eq, sel, own);
-        } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
-            k.pc[off - k.off] ^= mc_finish(eq, own, sel, g.tab, g.head, g.seed, mc_word_id(yw, g), g.c3_base);
-        }
-    }
-    k.n_queued += __popc(pend);
-}
+__device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g) { return (k.yw & g.yw_mask) | g.wid_c; }
 
 // NZ < 0: any thresholds;  NZ = 0..3: thresholds with T4 < 1/4 whose planes 2 and 3 are NZ (see mc_compare4_nz)
 // CHK: the thread may have fewer rows than the loop runs steps (it >= n_act: step predicated off)
-// The in-row neighbour of a site is at index x'+1 in an A row ((y + colour) odd) and at x'-1 in a B row.
-template <int WT, bool B32, int NZ, bool CHK>
-__device__ __forceinline__ void mc_pair(McWalk &k, const McConst &g, int it) {
-    McPairOut o;
-    o.eq_a = o.sel_a = o.eq_b = o.sel_b = o.own_b = 0u;
+template <int WT, int P, bool B32, int NZ, bool CHK>
+__device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
+    uint32_t eq = 0, sel = 0;
     if (!CHK || it < g.n_act) {
-        const int W = WT > 0 ? WT : g.W;
-        const uint32_t ta = k.pc[0], tb = k.pc[W];
-        const uint32_t nb0 = k.po[W];      // other colour, row B: below the A row, beside the B row
-        const uint32_t db = k.po[2 * W];   // other colour, row below the B row
+        const uint32_t t = *k.pc;
+        const uint32_t d = k.po[g.W];
+        uint32_t n1;
         // in-row neighbour word w +- 1 (periodic): with W known at compile time the two possible offsets are immediates and
         // the choice is a predicate (the compiler otherwise recomputes the offset every row to save a register)
-        const uint32_t na = WT > 1 ? (g.w_last ? k.po[1 - WT] : k.po[1]) : k.po[g.d_up];
-        const uint32_t nb = WT > 1 ? (g.w_first ? k.po[W + WT - 1] : k.po[W - 1]) : k.po[W + g.d_dn];
-        const uint32_t n1a = B32 ? __funnelshift_r(k.n0, na, 1) : shift_up_index(k.n0, na, g.bits, g.mask);
-        const uint32_t n1b = B32 ? __funnelshift_l(nb, nb0, 1) : shift_down_index(nb0, nb, g.bits, g.mask);
-        const uint32_t aa[4] = {ta ^ k.u ^ g.anti, ta ^ nb0 ^ g.anti, ta ^ k.n0 ^ g.anti, ta ^ n1a ^ g.anti};
-        const uint32_t ab[4] = {tb ^ k.n0 ^ g.anti, tb ^ db ^ g.anti, tb ^ nb0 ^ g.anti, tb ^ n1b ^ g.anti};
-        mc_pair_pass1<NZ>(aa, ab, B32 ? 0xFFFFFFFFu : g.mask, g.head, g.seed, mc_word_id(k.yw, g), mc_word_id(k.yw + (uint32_t)W, g),
-                          g.c3_base, g.tab, o);
-        k.pc[0] = ta ^ o.flip_a;
-        k.pc[W] = tb ^ o.flip_b;
-        k.u = nb0;
-        k.n0 = db;
+        if (P) {
+            const uint32_t nb = WT > 1 ? (g.w_last ? k.po[1 - WT] : k.po[1]) : k.po[g.d_up];
+            n1 = B32 ? __funnelshift_r(k.n0, nb, 1) : shift_up_index(k.n0, nb, g.bits, g.mask);
+        } else {
+            const uint32_t nb = WT > 1 ? (g.w_first ? k.po[WT - 1] : k.po[-1]) : k.po[g.d_dn];
+            n1 = B32 ? __funnelshift_l(nb, k.n0, 1) : shift_down_index(k.n0, nb, g.bits, g.mask);
+        }
+        const uint32_t a1 = t ^ k.u ^ g.anti, a2 = t ^ d ^ g.anti, a3 = t ^ k.n0 ^ g.anti, a4 = t ^ n1 ^ g.anti;
+        uint32_t ge2;                       // A >= 2: these lanes flip unconditionally; sel: A == 1
+        mc_neighbour_count(a1, a2, a3, a4, ge2, sel);
+        eq = ~ge2;                          // A == 1 or A == 0: lanes that need a random number
+        if (!B32) {
+            ge2 &= g.mask;
+            sel &= g.mask;
+            eq &= g.mask;
+        }
+        uint32_t lt = 0;                    // subset of the initial eq, hence disjoint from the A >= 2 lanes
+        const uint32_t word_id = mc_word_id(k, g);
+        U4 r0, r1;
+        mc_philox_pair(g.head, g.seed, word_id, g.c3_base, r0, r1);
+        if (NZ >= 0) mc_compare4_nz<NZ>(r0, sel, eq, lt);
+        else mc_compare4(r0, g.tab, 0, sel, eq, lt);
+        mc_compare4(r1, g.tab, 4, sel, eq, lt);
+        *k.pc = t ^ (ge2 | lt);
+        k.u = k.n0;
+        k.n0 = d;
     }
-    // ~10 % of the words keep undecided lanes, i.e. almost every warp-row has a few: keep these blocks short
-    mc_push(k, g, o.eq_a != 0u, k.off, o.eq_a, o.sel_a, 0u, k.yw);
-    mc_push(k, g, (o.eq_b | o.own_b) != 0u, k.off + (uint32_t)g.W, o.eq_b, o.sel_b, o.own_b, k.yw + (uint32_t)g.W);
-    k.pc += 2 * g.W;
-    k.po += 2 * g.W;
-    k.off += 2u * (uint32_t)g.W;
-    k.yw += 2u * (uint32_t)g.W;
+    // ~10 % of the words keep undecided lanes, i.e. almost every warp-row has a few: keep this block short
+    const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);
+    if (eq != 0u) {
+        const int slot = k.n_queued + __popc(pend & g.lanes_below);
+        if (slot < g.qcap) {
+            g.my_q[slot] = make_uint4(k.off, eq, sel, 0u);
+        } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
+            *k.pc ^= mc_finish(eq, sel, 2, g.tab, g.head, g.seed, mc_word_id(k, g), g.c3_base);
+        }
+    }
+    k.n_queued += __popc(pend);
+    k.pc += g.W;
+    k.po += g.W;
+    k.off += (uint32_t)g.W;
+    k.yw += (uint32_t)g.W;
+}
+
+template <int WT, int P0, bool B32, int NZ, bool CHK>
+__device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
+    for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
+        mc_row<WT, P0, B32, NZ, CHK>(k, g, it);
+        mc_row<WT, 1 - P0, B32, NZ, CHK>(k, g, it + 1);
+    }
 }
 
 template <int WT, bool B32, int NZ, bool CHK>
-__device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
-    for (int it = 0; it < n_steps; it += 2) mc_pair<WT, B32, NZ, CHK>(k, g, it);  // n_steps is even
+__device__ __forceinline__ void mc_walk_par(int par0, McWalk &k, const McConst &g, int n_steps) {
+    if (par0) mc_walk<WT, 1, B32, NZ, CHK>(k, g, n_steps);
+    else mc_walk<WT, 0, B32, NZ, CHK>(k, g, n_steps);
 }
 
 template <int WT, bool CHK>
-__device__ __forceinline__ void mc_walk_b32(bool nz, int xy, McWalk &k, const McConst &g, int n_steps) {
-    if (!nz) mc_walk<WT, true, -1, CHK>(k, g, n_steps);
-    else if (xy == 0) mc_walk<WT, true, 0, CHK>(k, g, n_steps);
-    else if (xy == 1) mc_walk<WT, true, 1, CHK>(k, g, n_steps);
-    else if (xy == 2) mc_walk<WT, true, 2, CHK>(k, g, n_steps);
-    else mc_walk<WT, true, 3, CHK>(k, g, n_steps);
+__device__ __forceinline__ void mc_walk_b32(bool nz, int xy, int par0, McWalk &k, const McConst &g, int n_steps) {
+    if (!nz) mc_walk_par<WT, true, -1, CHK>(par0, k, g, n_steps);
+    else if (xy == 0) mc_walk_par<WT, true, 0, CHK>(par0, k, g, n_steps);
+    else if (xy == 1) mc_walk_par<WT, true, 1, CHK>(par0, k, g, n_steps);
+    else if (xy == 2) mc_walk_par<WT, true, 2, CHK>(par0, k, g, n_steps);
+    else mc_walk_par<WT, true, 3, CHK>(par0, k, g, n_steps);
 }
 
 template <int WT>
@@ -340,17 +376,17 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     k.n0 = k.po[0];
     k.yw = (uint32_t)((s.y_first + lr0) << lw);
     k.n_queued = 0;
-    // lr_lo is an A row ((y + c) odd, the callers see to that) and every group starts an even number of rows below it
+    const int par0 = (s.y_first + lr0 + c) & 1;  // warp-uniform (W >= 32: one group per warp; W < 32: chunk even)
     // thresholds below 1/4 (every coupling of the critical region): cheaper first compare, see mc_compare4_nz
     const bool nz = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1] | tab->tm[2][1] | tab->tm[3][1]) == 0u;
     const int xy = (tab->tm[2][0] ? 2 : 0) | (tab->tm[3][0] ? 1 : 0);
     if (s.bits == 32) {
-        if (WT >= 32) mc_walk_b32<WT, false>(nz, xy, k, g, n_steps);        // W is a compile-time constant >= 32
-        else if (WT > 0) mc_walk_b32<WT, true>(nz, xy, k, g, n_steps);      // ... < 32
-        else if (whole_pairs) mc_walk_b32<0, false>(nz, xy, k, g, n_steps);
-        else mc_walk_b32<0, true>(nz, xy, k, g, n_steps);
+        if (WT >= 32) mc_walk_b32<WT, false>(nz, xy, par0, k, g, n_steps);        // W is a compile-time constant >= 32
+        else if (WT > 0) mc_walk_b32<WT, true>(nz, xy, par0, k, g, n_steps);      // ... < 32
+        else if (whole_pairs) mc_walk_b32<0, false>(nz, xy, par0, k, g, n_steps);
+        else mc_walk_b32<0, true>(nz, xy, par0, k, g, n_steps);
     } else {
-        mc_walk<0, false, -1, true>(k, g, n_steps);
+        mc_walk_par<0, false, -1, true>(par0, k, g, n_steps);
     }
     __syncwarp();
     const int total = min(k.n_queued, q.cap);
@@ -358,7 +394,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
         const uint4 ent = g.my_q[e];
         const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
         const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
-        plane_c[ent.x] ^= mc_finish(ent.y, ent.w, ent.z, tab, g.head, seed, word_id, g.c3_base);
+        plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, g.head, seed, word_id, g.c3_base);
     }
     __syncthreads();
 }
@@ -874,9 +910,8 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
 
 // ---- resident kernel: a whole replica (L <= RESIDENT_MAX_L) lives in one CTA's shared memory -------------------------
 // One launch = n_samples x { [measure level 0 + block, pyramid in shared memory, accumulate], m Metropolis sweeps }.
-// Local row lr holds global row y = lr-1; rows 0, L+1 and L+2 are periodic halo copies (of global rows L-1, 0, 1), refreshed
-// after every half-sweep (3W words) instead of recomputed.  Colour 1 updates local rows 1..L, colour 0 local rows 2..L+1:
-// its row pairs are (1,2), (3,4), .., (L-1, 0) in global rows, and the pair that wraps is taken at the bottom, on the copy.  Global memory is touched at the start (load), at the end (store, accumulator
+// Local row lr holds global row y = lr-1; rows 0 and L+1 are periodic halo copies, refreshed after every half-sweep
+// (2W words) instead of recomputed.  Global memory is touched at the start (load), at the end (store, accumulator
 // flush) and nowhere in between; the accumulators of the launch live in shared memory as exact 128-bit sums.
 //
 // Block size = the number of column walkers a half-sweep can keep busy (resident_threads).  Lattices up to 64^2 are one
@@ -893,7 +928,7 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
     __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
-    const int rows = L + 3;
+    const int rows = L + 2;
     const uint32_t replica = a.replica_base + (uint32_t)r;
     const unsigned long long t0 = *a.d_t + a.t_off;
     Strip0 s;
@@ -982,17 +1017,13 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
             // S_sh / red are rewritten only after the barriers inside the sweeps below (or at the loop top)
         }
         for (int h = 0; h < 2 * a.m; ++h) {
-            const int c = h & 1, lr_lo = 2 - c;  // the first row of a half-sweep is an A row: (y + c) odd, y = lr - 1
-            if (SMALL) mc_half_sweep_t<1>(s, c, lr_lo, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
-            else mc_half_sweep(s, c, lr_lo, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
-            uint32_t *pc = s0_plane(s, c);  // refresh this colour's periodic copies
-            for (int w = threadIdx.x; w < W; w += blockDim.x)
-                if (c == 0) pc[W + w] = pc[(L + 1) * W + w];  // global row 0 was updated on its copy
-            __syncthreads();
-            for (int w = threadIdx.x; w < 3 * W; w += blockDim.x) {
+            const int c = h & 1;
+            if (SMALL) mc_half_sweep_t<1>(s, c, 1, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
+            else mc_half_sweep(s, c, 1, L, lw, anti, &tab, q, a.seed, replica, t + (unsigned long long)(h >> 1));
+            uint32_t *pc = s0_plane(s, c);  // refresh this colour's periodic halo rows
+            for (int w = threadIdx.x; w < 2 * W; w += blockDim.x) {
                 if (w < W) pc[w] = pc[L * W + w];
-                else if (w < 2 * W) pc[(L + 1) * W + (w - W)] = pc[W + (w - W)];
-                else pc[(L + 2) * W + (w - 2 * W)] = pc[2 * W + (w - 2 * W)];
+                else pc[(L + 1) * W + (w - W)] = pc[W + (w - W)];
             }
             __syncthreads();
         }

@@ -105,7 +105,7 @@ struct ResidentLayout {
 };
 MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
     ResidentLayout o;
-    const int W = l0_words(L), words = (L + 3) * W, warps = threads / 32;
+    const int W = l0_words(L), words = (L + 2) * W, warps = threads / 32;
     o.cap = sweep0_queue_cap(words, warps);
     o.queue_off = (2 * words + 3) & ~3;
     o.bufA_off = o.queue_off + 4 * o.cap * warps;

@@ -117,78 +117,4 @@ MCRG_HD U4 mc_philox_j(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, u
     return mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, h.h1 ^ pl ^ (k1 + 0xBB67AE85u), h.l1, k0, k1);
 }
 
-// The per-plane threshold masks (bit k of T4 / T8 replicated over a word); the kernels keep the table in shared memory:
-// broadcast loads on the otherwise idle LSU pipe instead of shifts on the ALU pipe, which is the binding pipe.
-struct McTable {
-    uint32_t tm[32][2];  // [plane][0: T4 bit, 1: T8 bit] as 0 / 0xFFFFFFFF
-};
-
-MCRG_HD void mc_table_fill(McTable &tab, uint32_t T4, uint32_t T8) {
-    for (int k = 0; k < 32; ++k) {
-        tab.tm[k][0] = ((T4 >> (31 - k)) & 1u) ? 0xFFFFFFFFu : 0u;
-        tab.tm[k][1] = ((T8 >> (31 - k)) & 1u) ? 0xFFFFFFFFu : 0u;
-    }
-}
-
-// planes [plane0, plane0 + 4) for thresholds of any shape
-MCRG_HD void mc_compare4(const U4 &r, const McTable *tab, int plane0, uint32_t sel, uint32_t &eq, uint32_t &lt) {
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const uint32_t t4 = tab->tm[plane0 + e][0], t8 = tab->tm[plane0 + e][1];
-        const uint32_t tm = (sel & t4) | (~sel & t8);  // this lane's threshold bit (A==1 lanes: T4, A==0: T8)
-        lt |= eq & ~rr[e] & tm;                        // U bit 0 where T bit 1, prefix equal: U < T
-        eq &= ~(rr[e] ^ tm);
-    }
-}
-
-// ---- one row pair, one word column: what the sweep kernels execute (specification: metropolis_flip_pair, bitops.cuh) ----
-// Pass 1 = three Philox calls for the two words — call 0 of each and call 1 of the A row's word, which the B row shares on the
-// lanes the A row no longer needs — and eight lazily compared planes per word, straight-line.  What is left goes to pass 2.
-struct McPairOut {
-    uint32_t flip_a, eq_a, sel_a;         // A row: flips decided so far; lanes still undecided after planes 0-7 (next: its call 2)
-    uint32_t flip_b, eq_b, sel_b, own_b;  // B row likewise; own_b = lanes that could not share and start at their OWN call 1
-};
-
-// NZ < 0: any thresholds;  NZ = 0..3: thresholds with T4 < 1/4 whose planes 2 and 3 are NZ (mc_compare4_nz)
-// a1..a4 = t ^ neighbour ^ anti per row; `mask` = valid lanes of a word
-template <int NZ>
-MCRG_HD void mc_pair_pass1(const uint32_t aa[4], const uint32_t ab[4], uint32_t mask, const McPhiloxHead &h, uint64_t seed,
-                           uint32_t word_a, uint32_t word_b, uint32_t c3_base, const McTable *tab, McPairOut &o) {
-    uint32_t ge2a, ge2b;
-    mc_neighbour_count(aa[0], aa[1], aa[2], aa[3], ge2a, o.sel_a);
-    mc_neighbour_count(ab[0], ab[1], ab[2], ab[3], ge2b, o.sel_b);
-    uint32_t eqa = ~ge2a & mask, eqb = ~ge2b & mask;  // A == 1 or A == 0: lanes that need a random number
-    uint32_t lta = 0u, ltb = 0u;                      // subsets of the initial eq, hence disjoint from the A >= 2 lanes
-    U4 r0a, r1, r0b;
-    mc_philox_pair(h, seed, word_a, c3_base, r0a, r1);
-    r0b = mc_philox_j(h, seed, word_b, c3_base, 0);
-    if (NZ >= 0) {
-        mc_compare4_nz<NZ>(r0a, o.sel_a, eqa, lta);
-        mc_compare4_nz<NZ>(r0b, o.sel_b, eqb, ltb);
-    } else {
-        mc_compare4(r0a, tab, 0, o.sel_a, eqa, lta);
-        mc_compare4(r0b, tab, 0, o.sel_b, eqb, ltb);
-    }
-    const uint32_t und_a = eqa;  // the A row's lanes that use the shared call themselves
-    mc_compare4(r1, tab, 4, o.sel_a, eqa, lta);
-    o.own_b = eqb & und_a;
-    eqb &= ~und_a;
-    mc_compare4(r1, tab, 4, o.sel_b, eqb, ltb);
-    o.flip_a = (ge2a & mask) | lta;
-    o.eq_a = eqa;
-    o.flip_b = (ge2b & mask) | ltb;
-    o.eq_b = eqb;
-}
-
-// pass 2, one word: lanes `own` start at the word's own call 1 (planes 4-7), lanes `eq` at call 2; returns the flips
-MCRG_HD uint32_t mc_finish(uint32_t eq, uint32_t own, uint32_t sel, const McTable *tab, const McPhiloxHead &h, uint64_t seed,
-                           uint32_t word_id, uint32_t c3_base) {
-    uint32_t lt = 0u;
-    if (own != 0u) mc_compare4(mc_philox_j(h, seed, word_id, c3_base, 1), tab, 4, sel, own, lt);
-    eq |= own;
-    for (int j = 2; j < 8 && eq != 0u; ++j) mc_compare4(mc_philox_j(h, seed, word_id, c3_base, j), tab, 4 * j, sel, eq, lt);
-    return lt;
-}
-
 }  // namespace mcrg

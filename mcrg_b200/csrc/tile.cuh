@@ -75,28 +75,21 @@ MCRG_HD void measure_pair0(const Strip0 &s, int lr0, int w, Counts &cnt, uint32_
     majority4(b0, w0, b1, w1, maj, tie);
 }
 
-// One Metropolis update of a row pair, one word column, in place: colour c, local rows lr (the A row: (y + c) odd) and lr + 1
-// (needs rows lr-1 .. lr+2 of the other colour).  See metropolis_flip_pair (bitops.cuh) for the pairing.
-MCRG_HD void update_pair0(const Strip0 &s, int c, int lr, int w, const McParams &p, uint32_t replica, uint64_t sweep) {
+// One Metropolis word update, in place: colour c, local row lr (needs rows lr-1 and lr+1 of the other colour).
+MCRG_HD void update_word0(const Strip0 &s, int c, int lr, int w, const McParams &p, uint32_t replica,
+                          uint64_t sweep) {
     const int o = 1 - c;
-    uint32_t t[2], u[2], d[2], n0[2], n1[2], word_id[2];
-    for (int r = 0; r < 2; ++r) {
-        const int l = lr + r;
-        int y = s.y_first + l;
-        if (y >= s.L) y -= s.L;
-        if (y >= s.L) y %= s.L;
-        t[r] = s0_get(s, c, l, w);
-        u[r] = s0_get(s, o, l - 1, w);
-        d[r] = s0_get(s, o, l + 1, w);
-        n0[r] = s0_get(s, o, l, w);
-        n1[r] = ((y + c) & 1) ? s0_up(s, o, l, w) : s0_dn(s, o, l, w);
-        word_id[r] = (uint32_t)(((size_t)c * s.L + y) * s.W + w);
-    }
-    uint32_t fa, fb;
-    metropolis_flip_pair(t[0], u[0], d[0], n0[0], n1[0], t[1], u[1], d[1], n0[1], n1[1], s.mask, p, word_id[0], word_id[1], replica,
-                         sweep, fa, fb);
-    s.base[(c * s.rows + lr) * s.W + w] = t[0] ^ fa;
-    s.base[(c * s.rows + lr + 1) * s.W + w] = t[1] ^ fb;
+    int y = s.y_first + lr;
+    if (y >= s.L) y -= s.L;
+    if (y >= s.L) y %= s.L;
+    const uint32_t t = s0_get(s, c, lr, w);
+    const uint32_t u = s0_get(s, o, lr - 1, w);
+    const uint32_t d = s0_get(s, o, lr + 1, w);
+    const uint32_t n0 = s0_get(s, o, lr, w);
+    const uint32_t n1 = ((y + c) & 1) ? s0_up(s, o, lr, w) : s0_dn(s, o, lr, w);
+    const uint32_t word_id = (uint32_t)(((size_t)c * s.L + y) * s.W + w);
+    const uint32_t flip = metropolis_flip_mask(t, u, d, n0, n1, s.mask, p, word_id, replica, sweep);
+    s.base[(c * s.rows + lr) * s.W + w] = t ^ flip;
 }
 
 // ---- blocked levels: natural layout ----------------------------------------------------------------------------

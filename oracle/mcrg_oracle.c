@@ -372,7 +372,8 @@ void orc_hot_start(int L, uint64_t seed, uint32_t replica, int32_t *spins) {
         }
 }
 
-/* four bits (MSB first) for `lane` from call j of Philox word `word`: element e supplies bit 3 - e */
+/* uniform U in [0,2^32) for (site, sweep): bit k (MSB first) is bit `lane` of the k-th Philox output word of
+ * that site's packed word, output word k = call (k>>2), element (k&3).  mc_four_bits returns the four bits call j supplies. */
 static uint32_t mc_four_bits(uint64_t seed, uint32_t word, int lane, uint32_t replica, uint64_t t, int j) {
     uint32_t r[4], v = 0;
     orc_philox_keyed(seed, word, replica, t, ORC_PURPOSE_MC, j, r);
@@ -380,74 +381,43 @@ static uint32_t mc_four_bits(uint64_t seed, uint32_t word, int lane, uint32_t re
     return v;
 }
 
-/* number of bonds of site (x, y) that a flip would repair */
-static int mc_repairable(int L, const int32_t *spins, int x, int y, int ferro) {
-    const int32_t s = spins[(size_t)y * L + x];
-    const int yp = (y + 1) % L, ym = (y + L - 1) % L, xp = (x + 1) % L, xm = (x + L - 1) % L;
-    const int32_t nb[4] = {spins[(size_t)ym * L + x], spins[(size_t)yp * L + x], spins[(size_t)y * L + xm], spins[(size_t)y * L + xp]};
-    int A = 0; /* unfavourable bonds: anti-aligned if ferro */
-    for (int k = 0; k < 4; ++k) A += ferro ? (nb[k] != s) : (nb[k] == s);
-    return A;
-}
-
-/* Scalar specification of the checkerboard Metropolis sweep (what the CUDA kernels must reproduce bit for bit).
- * Site (x, y) of colour c = (x+y)&1 sits in packed word (c, y, x' >> 5), lane x' & 31, x' = x >> 1.  It flips always if A >= 2
- * (A = bonds the flip repairs), else iff U < T4 (A == 1) / U < T8 (A == 0) with a 32-bit uniform U assembled MSB first from
- * Philox bit planes:
- *   bits 0-3    call j = 0 of the site's own word;
- *   bits 4-7    the rows of a colour come in pairs (A row: (y + c) odd; B row: y + 1 mod L).  An A-row site takes call
- *               j = 1 of its own word.  A B-row site takes call j = 1 of the A row's word at the same (word, lane) — unless
- *               that A-row site is itself still undecided after its bits 0-3 (it needs a random number, A <= 1, and its
- *               four bits equal the leading four bits of its threshold), in which case the B-row site takes call j = 1
- *               of its own word;
- *   bits 8-31   calls j = 2 .. 7 of the site's own word.
- * All states are those at the start of the half-sweep (sites of one colour do not interact).  No random bit is read by two
- * sites, and which site reads it never depends on the bit itself, so every U is uniform and independent of the others. */
 void orc_metropolis(int L, int32_t *spins, double K, uint64_t seed, uint32_t replica, uint64_t t0, int n_sweeps) {
     uint32_t T4, T8;
     orc_thresholds(K, &T4, &T8);
-    const int ferro = (K <= 0.0);
-    int32_t *prev = (int32_t *)malloc(sizeof(int32_t) * (size_t)L * L);
+    int ferro = (K <= 0.0);
     for (int sw = 0; sw < n_sweeps; ++sw) {
-        const uint64_t t = t0 + (uint64_t)sw;
+        uint64_t t = t0 + (uint64_t)sw;
         for (int c = 0; c < 2; ++c) {
-            memcpy(prev, spins, sizeof(int32_t) * (size_t)L * L);
             for (int y = 0; y < L; ++y)
                 for (int x = 0; x < L; ++x) {
                     if (((x + y) & 1) != c) continue;
-                    const int A = mc_repairable(L, prev, x, y, ferro);
+                    int32_t s = spins[(size_t)y * L + x];
+                    int yp = (y + 1) % L, ym = (y + L - 1) % L, xp = (x + 1) % L, xm = (x + L - 1) % L;
+                    int32_t nb[4] = {spins[(size_t)ym * L + x], spins[(size_t)yp * L + x], spins[(size_t)y * L + xm],
+                                     spins[(size_t)y * L + xp]};
+                    int A = 0; /* unfavourable bonds that the flip would repair: anti-aligned if ferro */
+                    for (int k = 0; k < 4; ++k) A += ferro ? (nb[k] != s) : (nb[k] == s);
                     int flip;
                     if (A >= 2) flip = 1;
                     else {
+                        /* flip = U < T with the 32-bit uniform U of this (site, sweep), compared four bits at a time, MSB
+                         * first: the first differing group decides, so most sites need one Philox call, not eight */
                         const uint32_t T = (A == 1) ? T4 : T8;
-                        const int xh = x >> 1, lane = xh & 31;
-                        const uint32_t own = mc_word_id(L, c, y, xh);
+                        const int xh = x >> 1;
+                        const uint32_t word = mc_word_id(L, c, y, xh);
                         flip = 0; /* U == T is not an acceptance */
-                        for (int j = 0; j < 8; ++j) { /* U < T, four bits at a time, MSB first */
-                            uint32_t source = own;
-                            if (j == 1 && ((y + c) & 1) == 0) { /* B row: its partner is the site with the same x' in the row above */
-                                const int ya = (y + L - 1) % L, xa = 2 * xh + 1; /* A row: (ya + c) odd, sites x = 2x' + 1 */
-                                const uint32_t wa = mc_word_id(L, c, ya, xh);
-                                const int Aa = mc_repairable(L, prev, xa, ya, ferro);
-                                int a_undecided = 0;
-                                if (Aa <= 1) {
-                                    const uint32_t Ta = (Aa == 1) ? T4 : T8;
-                                    a_undecided = mc_four_bits(seed, wa, lane, replica, t, 0) == (Ta >> 28);
-                                }
-                                if (!a_undecided) source = wa;
-                            }
-                            const uint32_t u4 = mc_four_bits(seed, source, lane, replica, t, j), t4 = (T >> (28 - 4 * j)) & 15u;
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t u4 = mc_four_bits(seed, word, xh & 31, replica, t, j), t4 = (T >> (28 - 4 * j)) & 15u;
                             if (u4 != t4) {
                                 flip = u4 < t4;
                                 break;
                             }
                         }
                     }
-                    if (flip) spins[(size_t)y * L + x] = -prev[(size_t)y * L + x];
+                    if (flip) spins[(size_t)y * L + x] = -s;
                 }
         }
     }
-    free(prev);
 }
 
 static int uf_find(int *parent, int x) {

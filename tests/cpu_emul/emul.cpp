@@ -70,9 +70,8 @@ void sweep0(Emu &e, int R, int nsw, bool measure) {
         if (nsw > 0) {
             for (int h = 0; h < 2 * nsw; ++h) {
                 const int c = h & 1;
-                // the region of half-sweep h starts on an A row ((y + c) odd: y0, H even, h = c mod 2) and holds whole pairs
-                for (int lr = 1 + h; lr < rows - 1 - h; lr += 2)
-                    for (int w = 0; w < W; ++w) update_pair0(s, c, lr, w, e.mc, e.replica, e.t + (uint64_t)(h >> 1));
+                for (int lr = 1 + h; lr < rows - 1 - h; ++lr)
+                    for (int w = 0; w < W; ++w) update_word0(s, c, lr, w, e.mc, e.replica, e.t + (uint64_t)(h >> 1));
             }
             for (int c = 0; c < 2; ++c)
                 for (int lr = 0; lr < R; ++lr)
@@ -258,15 +257,26 @@ void emul_hot_start(int L, uint64_t seed, uint32_t replica, int32_t *spins) {
 }
 
 // ---- fast forms of the per-word arithmetic (mcfast.cuh) against the specification (bitops.cuh) -----------------------
-// The sweep kernels do not call philox4x32_10 / metropolis_flip_pair: they share the word-independent part of Philox
-// rounds 0-1 between calls, count broken bonds with a full adder, compare the first call's planes with code specialised on
-// the leading threshold bits and split the work in two passes (mc_pair_pass1 / mc_finish).  Random words, keys and thresholds of every pattern: both ways must agree
+// The sweep kernels do not call philox4x32_10 / metropolis_flip_mask: they share the word-independent part of Philox
+// rounds 0-1 between calls, count broken bonds with a full adder and compare the first call's planes with code
+// specialised on the leading threshold bits.  Random words, keys and thresholds of every pattern: both ways must agree
 // on every bit.  Returns the number of disagreements.
 static uint64_t splitmix(uint64_t &x) {
     uint64_t z = (x += 0x9E3779B97F4A7C15ull);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
+}
+
+static void cmp4_generic(const U4 &r, uint32_t T4, uint32_t T8, int plane0, uint32_t sel, uint32_t &eq, uint32_t &lt) {
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    for (int e = 0; e < 4; ++e) {
+        const int k = plane0 + e;
+        const uint32_t t4 = ((T4 >> (31 - k)) & 1u) ? 0xFFFFFFFFu : 0u, t8 = ((T8 >> (31 - k)) & 1u) ? 0xFFFFFFFFu : 0u;
+        const uint32_t tm = (sel & t4) | (~sel & t8);
+        lt |= eq & ~rr[e] & tm;
+        eq &= ~(rr[e] ^ tm);
+    }
 }
 
 static bool same(const U4 &a, const U4 &b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
@@ -286,7 +296,7 @@ int emul_fast_paths(int n_trials, uint64_t seed0) {
         if (!same(r1, philox_keyed(seed, word, replica, t, PURPOSE_MC, 1))) ++bad;
         for (int j = 0; j < 8; ++j)
             if (!same(mc_philox_j(h, seed, word, c3_base, j), philox_keyed(seed, word, replica, t, PURPOSE_MC, j))) ++bad;
-        // (2) one row-pair update: thresholds of every leading-bit pattern (and general ones), spins near and far from order
+        // (2) one word update: thresholds of every leading-bit pattern (and general ones), spins near and far from order
         McParams p;
         p.seed = seed;
         p.anti = (splitmix(x) & 1) ? 0xFFFFFFFFu : 0u;
@@ -301,41 +311,32 @@ int emul_fast_paths(int n_trials, uint64_t seed0) {
             p.T4 = (uint32_t)splitmix(x) & 0xFFFFu;
             p.T8 = (uint32_t)splitmix(x) & 0xFFu;
         }
-        if ((it & 63) == 5) p.T4 = p.T8 = 0xFFFFFFFFu;  // every plane ties with probability 1/2: long lazy comparisons, many lanes
-        if ((it & 63) == 6) p.T4 = p.T8 = 0u;           // that cannot share the second call
-        const uint32_t word_b = (uint32_t)splitmix(x) & 0x3FFFFFFu;
-        const uint32_t mask = (it % 11 == 0) ? valid_mask(1 + (int)(splitmix(x) % 31)) : 0xFFFFFFFFu;  // short rows (L < 64) too
-        uint32_t tw[2], nb[2][4], aa[2][4];
-        for (int r = 0; r < 2; ++r) {
-            tw[r] = (uint32_t)splitmix(x);
-            for (int k = 0; k < 4; ++k) {  // neighbours = the word itself with a sparse, dense or random set of differences
-                const uint32_t m1 = (uint32_t)splitmix(x), m2 = (uint32_t)splitmix(x), m3 = (uint32_t)splitmix(x);
-                const int kind = (int)(splitmix(x) % 3);
-                nb[r][k] = (tw[r] ^ p.anti) ^ (kind == 0 ? (m1 & m2 & m3) : kind == 1 ? (m1 | m2) : m1);
-                aa[r][k] = tw[r] ^ nb[r][k] ^ p.anti;
-            }
+        const uint32_t tw = (uint32_t)splitmix(x);
+        uint32_t nb[4];
+        for (int k = 0; k < 4; ++k) {  // neighbours = the word itself with a sparse, dense or random set of differences
+            const uint32_t m1 = (uint32_t)splitmix(x), m2 = (uint32_t)splitmix(x), m3 = (uint32_t)splitmix(x);
+            const int kind = (int)(splitmix(x) % 3);
+            nb[k] = (tw ^ p.anti) ^ (kind == 0 ? (m1 & m2 & m3) : kind == 1 ? (m1 | m2) : m1);
         }
-        uint32_t want_a, want_b;
-        metropolis_flip_pair(tw[0], nb[0][0], nb[0][1], nb[0][2], nb[0][3], tw[1], nb[1][0], nb[1][1], nb[1][2], nb[1][3], mask, p, word,
-                             word_b, replica, t, want_a, want_b);
-        McTable tab;
-        mc_table_fill(tab, p.T4, p.T8);
-        McPairOut o;
+        const uint32_t want = metropolis_flip_mask(tw, nb[0], nb[1], nb[2], nb[3], 0xFFFFFFFFu, p, word, replica, t);
+        const uint32_t a1 = tw ^ nb[0] ^ p.anti, a2 = tw ^ nb[1] ^ p.anti, a3 = tw ^ nb[2] ^ p.anti, a4 = tw ^ nb[3] ^ p.anti;
+        uint32_t ge2, sel;
+        mc_neighbour_count(a1, a2, a3, a4, ge2, sel);
+        uint32_t eq = ~ge2, lt = 0u;
         const bool nz = (p.T4 >> 30) == 0u && (p.T8 >> 28) == 0u;
         if (nz) {
             switch ((p.T4 >> 28) & 3u) {
-                case 0: mc_pair_pass1<0>(aa[0], aa[1], mask, h, seed, word, word_b, c3_base, &tab, o); break;
-                case 1: mc_pair_pass1<1>(aa[0], aa[1], mask, h, seed, word, word_b, c3_base, &tab, o); break;
-                case 2: mc_pair_pass1<2>(aa[0], aa[1], mask, h, seed, word, word_b, c3_base, &tab, o); break;
-                default: mc_pair_pass1<3>(aa[0], aa[1], mask, h, seed, word, word_b, c3_base, &tab, o); break;
+                case 0: mc_compare4_nz<0>(r0, sel, eq, lt); break;
+                case 1: mc_compare4_nz<1>(r0, sel, eq, lt); break;
+                case 2: mc_compare4_nz<2>(r0, sel, eq, lt); break;
+                default: mc_compare4_nz<3>(r0, sel, eq, lt); break;
             }
         } else {
-            mc_pair_pass1<-1>(aa[0], aa[1], mask, h, seed, word, word_b, c3_base, &tab, o);
+            cmp4_generic(r0, p.T4, p.T8, 0, sel, eq, lt);
         }
-        const uint32_t got_a = o.flip_a | mc_finish(o.eq_a, 0u, o.sel_a, &tab, h, seed, word, c3_base);
-        const uint32_t got_b = o.flip_b | mc_finish(o.eq_b, o.own_b, o.sel_b, &tab, h, seed, word_b, c3_base);
-        if (got_a != want_a) ++bad;
-        if (got_b != want_b) ++bad;
+        cmp4_generic(r1, p.T4, p.T8, 4, sel, eq, lt);
+        for (int j = 2; j < 8 && eq != 0u; ++j) cmp4_generic(mc_philox_j(h, seed, word, c3_base, j), p.T4, p.T8, 4 * j, sel, eq, lt);
+        if ((ge2 | lt) != want) ++bad;
     }
     return bad;
 }
