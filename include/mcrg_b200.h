@@ -121,6 +121,14 @@ int mcrg_sweep(mcrg_ctx *ctx, int n_sweeps);
 int mcrg_measure(mcrg_ctx *ctx, int max_levels, int64_t *S, int *n_lv_out);
 /* level-0 sums per replica: calc_interactions, calc_nearest_neighbor_interaction (lattice.cpp:84-120), the
  * spin sum behind calc_magnetization (ising.cpp:176-179) and the plaquette sum.  Any pointer may be NULL. */
+/* tie_mode = supplied ("teacher forcing" through the ABI): the same measurement with the CALLER's tie coins
+ * instead of the Philox ones, so that the device's block spins can be compared bit for bit with lattices whose ties were
+ * drawn elsewhere — e.g. by the reference's own rng (mcrg.cpp:333-335).  tie_bits: per replica mcrg_tie_words(L, max_levels)
+ * words = the packed coin words of levels 1, 2, .. laid end to end, each in the natural layout of that output lattice
+ * (row = reference column jb, bit = reference row ib, max(1, Ln/32) words per row; bit 1 = the tied block becomes +1;
+ * bits of blocks that do not tie are ignored). */
+size_t mcrg_tie_words(int L, int max_levels);
+int mcrg_measure_supplied(mcrg_ctx *ctx, int max_levels, const uint32_t *tie_bits, int64_t *S, int *n_levels_out);
 int mcrg_observables(mcrg_ctx *ctx, int64_t *Snn, int64_t *Snnn, int64_t *Splaq, int64_t *M);
 /* the sample loop of calc_critical_exponent (mcrg.cpp:72-98), n_samples times for every replica:
  *   measure the current configuration at all levels, add S, S(n) x S(n-1), S(n) x S(n) into bin `bin`,

@@ -76,6 +76,9 @@ def lib():
         l.mcrg_sweep.argtypes = [vp, C.c_int]
         l.mcrg_measure.argtypes = [vp, C.c_int, vp, P(C.c_int)]
         l.mcrg_observables.argtypes = [vp, vp, vp, vp, vp]
+        l.mcrg_tie_words.argtypes = [C.c_int, C.c_int]
+        l.mcrg_tie_words.restype = C.c_size_t
+        l.mcrg_measure_supplied.argtypes = [vp, C.c_int, vp, vp, P(C.c_int)]
         l.mcrg_run.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         l.mcrg_profile_kernels.argtypes = [vp, C.c_int, C.c_int, C.c_int, P(C.c_float)]
         l.mcrg_probe_philox_rate.argtypes = [vp, P(C.c_double)]
@@ -280,6 +283,28 @@ class Context:
         S = np.zeros((self.n_replicas, n_lv + 1, NOBS), np.int64)
         got = C.c_int(0)
         _check(lib().mcrg_measure(self._h, max_levels, S.ctypes.data, C.byref(got)))
+        assert got.value == n_lv
+        return S
+
+    def measure_supplied(self, tie_levels, max_levels=-1):
+        """measure() with caller-supplied tie coins.  tie_levels[lv - 1]: int array [replica, Ln, Ln] (reference layout, arr[r, j, i]) of
+        +-1 (or 0/1) coins for the blocks of level lv = 1 .. n_lv; only the entries of tied blocks matter."""
+        n_lv = min(levels_full(self.L), max_levels) if max_levels >= 0 else levels_full(self.L)
+        per = lib().mcrg_tie_words(self.L, n_lv)
+        bits = np.zeros((self.n_replicas, max(per, 1)), np.uint32)
+        off = 0
+        for lv in range(1, n_lv + 1):
+            Ln = self.L >> lv
+            Wn = max(1, Ln // 32)
+            t = (np.asarray(tie_levels[lv - 1]).reshape(self.n_replicas, Ln, Ln) > 0)
+            for w in range(Wn):
+                chunk = t[:, :, 32 * w:32 * w + min(32, Ln)].astype(np.uint64)
+                words = (chunk << np.arange(chunk.shape[2], dtype=np.uint64)).sum(axis=2).astype(np.uint32)  # [replica, row]
+                bits[:, off + np.arange(Ln) * Wn + w] = words
+            off += Ln * Wn
+        S = np.zeros((self.n_replicas, n_lv + 1, NOBS), np.int64)
+        got = C.c_int(0)
+        _check(lib().mcrg_measure_supplied(self._h, max_levels, bits.ctypes.data, S.ctypes.data, C.byref(got)))
         assert got.value == n_lv
         return S
 

@@ -100,6 +100,8 @@ struct mcrg_ctx {
     int strip_rows = 0, fuse_sweeps = 1, use_graphs = 1;
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<int, int> auto_R;  // halo depth -> strip height chosen by choose_R
+    const uint32_t *ties = nullptr;  // caller-supplied tie coins of the measurement being enqueued (mcrg_measure_supplied)
+    size_t tie_stride = 0;
     int n_sm = 148;
 };
 
@@ -211,6 +213,8 @@ SweepArgs sweep_args(const mcrg_ctx *c, int R, int nsw, unsigned long long t_off
     a.src = c->planes[c->cur];
     a.dst = c->planes[1 - c->cur];
     a.level1 = level_ptr(c, 1, parity);
+    a.ties = c->ties;
+    a.tie_stride = c->tie_stride;
     a.cnt = cnt_ptr(c, parity);
     a.T4 = c->T4;
     a.T8 = c->T8;
@@ -308,6 +312,9 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
         LevelArgs la;
         la.in = level_ptr(c, lv, parity);
         la.out = lv < n_lv ? level_ptr(c, lv + 1, parity) : nullptr;
+        la.ties = c->ties;
+        la.tie_stride = c->tie_stride;
+        la.L = c->L;
         la.cnt = cnt_ptr(c, parity);
         la.d_t = c->d_t;
         la.t_off = t_off;
@@ -323,6 +330,8 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     TailArgs ta;
     ta.in = lv <= n_lv ? level_ptr(c, lv, parity) : nullptr;
     ta.levels_out = c->levels;
+    ta.ties = c->ties;
+    ta.tie_stride = c->tie_stride;
     ta.level_off = c->d_level_off;
     ta.cnt = cnt_ptr(c, parity);
     ta.S_out = c->S_out;
@@ -873,6 +882,33 @@ int mcrg_measure(mcrg_ctx *c, int max_levels, int64_t *S, int *n_lv_out) {
                     S[((size_t)r * (n_lv + 1) + lv) * 4 + k] = tmp[((size_t)r * (MAX_LEVELS + 1) + lv) * 4 + k];
     }
     return 0;
+}
+
+size_t mcrg_tie_words(int L, int max_levels) {
+    if (L < 2 || (L & (L - 1))) return 0;
+    int n_lv = ilog2h(L) - 1;
+    if (max_levels >= 0 && max_levels < n_lv) n_lv = max_levels;
+    return tie_level_off(L, n_lv + 1);
+}
+
+int mcrg_measure_supplied(mcrg_ctx *c, int max_levels, const uint32_t *tie_bits, int64_t *S, int *n_lv_out) {
+    if (!c || !tie_bits) return fail(MCRG_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    const int n_lv = clamp_levels(c, max_levels);
+    const size_t per = mcrg_tie_words(c->L, n_lv), words = per * (size_t)c->n_replicas;
+    uint32_t *dev = nullptr;
+    if (words > 0) {
+        CK(cudaMalloc(&dev, words * 4));
+        CK(cudaMemcpyAsync(dev, tie_bits, words * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->ties = dev;
+    c->tie_stride = per;
+    const int rc = mcrg_measure(c, max_levels, S, n_lv_out);
+    c->ties = nullptr;
+    c->tie_stride = 0;
+    cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    return rc;
 }
 
 int mcrg_observables(mcrg_ctx *c, int64_t *Snn, int64_t *Snnn, int64_t *Splaq, int64_t *M) {

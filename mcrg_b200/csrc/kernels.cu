@@ -445,7 +445,8 @@ __device__ __forceinline__ uint32_t measure_item_b32(const uint32_t *pb, const u
 
 template <int WT, bool FAST4>
 __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R, int lw, int y0, uint32_t *lev1, uint64_t seed,
-                                                  uint32_t replica, unsigned long long t, Counts &cnt) {
+                                                  uint32_t replica, unsigned long long t, Counts &cnt,
+                                                  const uint32_t *tie_src = nullptr) {
     const int W = WT > 0 ? WT : s.W;
     const int w = threadIdx.x & (W - 1), i0 = threadIdx.x >> lw, di = blockDim.x >> lw;  // blockDim is a multiple of W
     const int d_up = ((w + 1) & (W - 1)) - w, d_dn = ((w - 1) & (W - 1)) - w;
@@ -456,7 +457,7 @@ __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R,
     const uint32_t dq = (uint32_t)(di << lw);
     MeasureAcc m = {0u, 0u, 0u, 0u};
     const int half = R >> 1;
-    if (FAST4 && blockDim.x == 256) {
+    if (FAST4 && blockDim.x == 256 && tie_src == nullptr) {
         // The CTA's 256 threads x 4 items cover one 1024-word chunk of level-1 output (4 * di pair rows): a thread's items are
         // the words q = 1024 c + threadIdx.x + 256 e, e = 0..3 — exactly the four words that share one tie-coin call
         // (tie_group), in the order x, y, z, w.  Chunks are aligned to the LATTICE (not to the strip), so a strip of any even
@@ -485,7 +486,7 @@ __device__ __forceinline__ void measure_strip_b32(const Strip0 &s, int H, int R,
         for (int i = i0; i < half; i += di, pb += step, pw += step, q += dq) {
             uint32_t tie;
             uint32_t maj = measure_item_b32<WT>(pb, pw, W, d_up, d_dn, m, tie);
-            if (tie) maj |= tie & coins.get(seed, q, replica, t, 1);
+            if (tie) maj |= tie & (tie_src ? tie_src[q] : coins.get(seed, q, replica, t, 1));
             lev1[q] = maj;
         }
     }
@@ -583,9 +584,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
         Counts c = {0u, 0u, 0u, 0u};
         const int npairs = (Rs >> 1) << lw;
         uint32_t *lev1 = a.level1 + (size_t)r * (L >> 1) * W;
+        const uint32_t *tie_src = a.ties ? a.ties + (size_t)r * a.tie_stride : nullptr;  // level 1 comes first
         if (a.bits == 32) {  // L >= 64
-            if (W == 64) measure_strip_b32<64, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c);  // L = 4096
-            else measure_strip_b32<0, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c);
+            if (W == 64) measure_strip_b32<64, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c, tie_src);  // L = 4096
+            else measure_strip_b32<0, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c, tie_src);
         } else {
             TieCache coins;
             coins.init();
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
                 measure_pair0(s, a.H + 2 * i, w, c, maj, tie);
                 const uint32_t q = (uint32_t)(((y0 >> 1) + i) << lw) + (uint32_t)w;
                 uint32_t out = maj;
-                if (tie) out |= tie & coins.get(a.seed, q, replica, t, 1);
+                if (tie) out |= tie & (tie_src ? tie_src[q] : coins.get(a.seed, q, replica, t, 1));
                 lev1[q] = out;
             }
         }
@@ -655,6 +657,7 @@ __global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_l
     if (a.out != nullptr) {
         const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
         uint32_t *out_r = a.out + (size_t)r * Lb * Wb;
+        const uint32_t *tie_src = a.ties ? a.ties + (size_t)r * a.tie_stride + tie_level_off(a.L, a.level + 1) : nullptr;
         const int nb = (a.R >> 1) << lwb;
         TieCache coins;
         coins.init();
@@ -671,7 +674,7 @@ __global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_l
                     uint32_t maj, tie;
                     block_pairN(s, 2 * i, wb, maj, tie);
                     uint32_t o = maj;
-                    if (tie) o |= tie & coins.get(a.seed, q, replica, t, a.level + 1);
+                    if (tie) o |= tie & (tie_src ? tie_src[q] : coins.get(a.seed, q, replica, t, a.level + 1));
                     out_r[q] = o;
                 }
     }
@@ -689,7 +692,7 @@ __global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_l
 // this; ends synchronised.
 __device__ __forceinline__ void pyramid_tail_warp(const uint32_t *cur, int L, int lv0, int n_levels, unsigned int *red,
                                                   uint32_t *levels_out, const size_t *level_off, int r, uint64_t seed,
-                                                  uint32_t replica, unsigned long long t) {
+                                                  uint32_t replica, unsigned long long t, const uint32_t *ties) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         int Ln = L >> lv0;
@@ -707,7 +710,7 @@ __device__ __forceinline__ void pyramid_tail_warp(const uint32_t *cur, int L, in
                 }
                 base += n;
             }
-            if (my_lv >= 0) coin = tie_word(seed, (uint32_t)my_q, replica, t, my_lv);
+            if (my_lv >= 0) coin = ties ? ties[tie_level_off(L, my_lv) + (size_t)my_q] : tie_word(seed, (uint32_t)my_q, replica, t, my_lv);
         }
         int coin_base = 0;
         for (int lv = lv0; lv <= n_levels; ++lv, Ln >>= 1) {
@@ -749,11 +752,11 @@ __device__ __forceinline__ void pyramid_tail_warp(const uint32_t *cur, int L, in
 // every produced level to global memory.  All threads of the CTA call this; ends synchronised.
 __device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, int L, int start, int n_levels, unsigned int *red,
                                                 uint32_t *levels_out, const size_t *level_off, int r, uint64_t seed,
-                                                uint32_t replica, unsigned long long t) {
+                                                uint32_t replica, unsigned long long t, const uint32_t *ties = nullptr) {
     for (int lv = start; lv <= n_levels; ++lv) {
         const int Ln = L >> lv, Wn = nat_words(Ln), lw = ilog2(Wn);
         if (Ln <= 32) {  // one word per row and at most 32 rows: the rest of the pyramid is one warp's business
-            pyramid_tail_warp(cur, L, lv, n_levels, red, levels_out, level_off, r, seed, replica, t);
+            pyramid_tail_warp(cur, L, lv, n_levels, red, levels_out, level_off, r, seed, replica, t, ties);
             return;
         }
         StripN s;
@@ -768,6 +771,7 @@ __device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, in
             const int Lb = Ln >> 1, Wb = nat_words(Lb), lwb = ilog2(Wb);
             uint32_t *glob = levels_out ? levels_out + level_off[lv + 1] + (size_t)r * Lb * Wb : nullptr;
             const int nb = Lb << lwb;
+            const uint32_t *tie_src = ties ? ties + tie_level_off(L, lv + 1) : nullptr;
             TieCache coins;
             coins.init();
             for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
@@ -775,7 +779,7 @@ __device__ __forceinline__ void pyramid_in_smem(uint32_t *cur, uint32_t *nxt, in
                 uint32_t maj, tie;
                 block_pairN(s, 2 * yb, wb, maj, tie);
                 uint32_t o = maj;
-                if (tie) o |= tie & coins.get(seed, (uint32_t)idx, replica, t, lv + 1);
+                if (tie) o |= tie & (tie_src ? tie_src[idx] : coins.get(seed, (uint32_t)idx, replica, t, lv + 1));
                 nxt[idx] = o;
                 if (glob) glob[idx] = o;
             }
@@ -875,7 +879,8 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
         tile_stage_wait(tma, &bar);
     }
     __syncthreads();
-    pyramid_in_smem(bufA, bufB, a.L, a.start, a.n_levels, red, a.levels_out, a.level_off, r, a.seed, replica, t);
+    pyramid_in_smem(bufA, bufB, a.L, a.start, a.n_levels, red, a.levels_out, a.level_off, r, a.seed, replica, t,
+                    a.ties ? a.ties + (size_t)r * a.tie_stride : nullptr);
     // raw popcounts -> the reference's sums; levels below `start` were counted by k_sweep0 / k_level
     if (threadIdx.x <= a.n_levels) {
         const int lv = threadIdx.x;

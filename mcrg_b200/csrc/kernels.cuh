@@ -40,6 +40,8 @@ struct SweepArgs {
     const uint32_t *src;       // planes [replica][colour][y][w]
     uint32_t *dst;
     uint32_t *level1;          // natural layout [replica][y][w] of the L/2 lattice (MEASURE only)
+    const uint32_t *ties;      // nullptr: Philox tie coins; else caller-supplied coins [replica][tie_stride] (mcrg_measure_supplied)
+    size_t tie_stride;
     unsigned long long *cnt;   // [replica][MAX_LEVELS+1][4] raw popcounts (MEASURE only)
     const uint32_t *T4, *T8, *anti;  // per replica
     const unsigned long long *d_t;   // device-resident sweep counter
@@ -54,6 +56,9 @@ struct SweepArgs {
 struct LevelArgs {
     const uint32_t *in;        // natural layout [replica][y][w], lattice size Ln
     uint32_t *out;             // natural layout of Ln/2 (nullptr: measure only)
+    const uint32_t *ties;      // as in SweepArgs
+    size_t tie_stride;
+    int L;                     // level-0 size (locates a level inside the supplied coins)
     unsigned long long *cnt;
     const unsigned long long *d_t;
     unsigned long long t_off;
@@ -66,6 +71,8 @@ struct LevelArgs {
 struct TailArgs {
     const uint32_t *in;        // level `start` lattice, natural layout [replica][y][w] (unused if start > n_levels)
     uint32_t *levels_out;      // base of the level buffers
+    const uint32_t *ties;      // as in SweepArgs
+    size_t tie_stride;
     const size_t *level_off;   // [MAX_LEVELS+1] word offset of each level's [replica][y][w] block
     unsigned long long *cnt;
     long long *S_out;          // [replica][MAX_LEVELS+1][4] converted sums of the last measurement
@@ -115,6 +122,14 @@ MCRG_HD ResidentLayout resident_layout(int L, int threads, int n_levels) {
     const int n_live = 6 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels;  // = acc_live_slots (kernels.cu)
     o.total_words = o.acc_off + 4 * n_live;
     return o;
+}
+
+// Caller-supplied tie coins (mcrg_measure_supplied): per replica the packed coin words of levels 1, 2, .. laid end to end,
+// each level in the natural layout of that (output) lattice.  Word offset of level lv >= 1:
+MCRG_HD size_t tie_level_off(int L, int lv) {
+    size_t off = 0;
+    for (int k = 1; k < lv; ++k) off += (size_t)(L >> k) * nat_words(L >> k);
+    return off;
 }
 
 // Swendsen-Wang cluster update (stands in for the reference's Wolff update, ising.cpp:87-155)

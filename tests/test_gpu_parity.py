@@ -221,6 +221,61 @@ def test_golden_reference_vectors(mc):
                 assert np.array_equal(got_blk[nontie], want_blk[nontie]), k
 
 
+def test_supplied_ties_reproduce_the_reference_block_lattice(mc):
+    """tie_mode = supplied (mcrg_measure_supplied): with the REFERENCE's own tie draws handed to the device, the level-1
+    lattice equals the reference's block_spin_transformation output on EVERY block, ties included
+    (tests/golden/deterministic.npz: block lattices made by the compiled reference with its global rng, mcrg.cpp:314-348)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "deterministic.npz"))
+    by_N = {}
+    for key in g["index"]:
+        N = int(str(key).split("_")[0][1:])
+        if N >= 4:
+            by_N.setdefault(N, []).append(str(key))
+    for N, keys in by_N.items():
+        spins = np.stack([np.where(np.unpackbits(g[k + "_bits"])[: N * N].reshape(N, N) > 0, 1, -1) for k in keys]).astype(np.int32)
+        blocks = np.stack([np.where(np.unpackbits(g[k + "_block_bits"])[: (N // 2) ** 2].reshape(N // 2, N // 2) > 0, 1, -1) for k in keys])
+        with mc.Context(N, len(keys), seed=1) as ctx:
+            ctx.set_spins(spins)
+            ctx.measure_supplied([blocks], max_levels=1)  # the reference's outputs serve as the coins of its tied blocks
+            for r, k in enumerate(keys):
+                assert np.array_equal(ctx.get_level_spins(r, 1), blocks[r]), k
+
+
+@pytest.mark.parametrize("L,strip", [(4, 0), (8, 0), (64, 0), (256, 0), (256, 16), (1024, 0), (2048, 44)])
+def test_supplied_ties_through_the_whole_pyramid(mc, L, strip):
+    """Random caller-supplied coins at every level, against the oracle's orc_block_spin_supplied chained down the pyramid:
+    every level's block spins and correlators (strip kernel, k_level, k_tail and the one-warp tail)."""
+    o = _libs.oracle()
+    rng = np.random.default_rng(L + strip)
+    cases = {"rand": _libs.random_lattice(L, 5), "checker": _libs.pattern_lattices(L)["checker"], "stripes": _libs.pattern_lattices(L)["stripes_i"]}
+    R = len(cases)
+    n_lv = int(np.log2(L)) - 1
+    coins = [np.where(rng.random((R, L >> lv, L >> lv)) < 0.5, 1, -1).astype(np.int32) for lv in range(1, n_lv + 1)]
+    with mc.Context(L, R, seed=3) as ctx:
+        ctx.set_tuning(strip_rows=strip)
+        ctx.set_spins(np.stack(list(cases.values())))
+        S = ctx.measure_supplied(coins)
+        for r, (name, s) in enumerate(cases.items()):
+            cur = np.ascontiguousarray(s)
+            for lv in range(0, n_lv + 1):
+                n = L >> lv
+                want = np.zeros(2, np.int64)
+                o.orc_calc_interactions(n, cur, want)
+                assert S[r, lv, 0] == want[0] and S[r, lv, 1] == want[1], (L, name, lv)
+                assert S[r, lv, 2] == o.orc_plaquette(n, cur) and S[r, lv, 3] == int(cur.sum()), (L, name, lv)
+                if lv == n_lv:
+                    break
+                nxt = np.zeros((n // 2, n // 2), np.int32)
+                mask = np.zeros((n // 2, n // 2), np.int32)
+                o.orc_block_spin_supplied(n, 2, cur, np.ascontiguousarray(coins[lv][r]), nxt, mask)
+                assert np.array_equal(ctx.get_level_spins(r, lv + 1), nxt), (L, name, lv + 1)
+                cur = nxt
+        # the Philox mode is untouched by a supplied-mode call
+        assert np.array_equal(ctx.measure()[0], _libs.pyramid(L, list(cases.values())[0], 3, 0, 0, -1))
+
+
 def test_tie_coins_are_fair_and_keyed(mc):
     L = 256
     s = _libs.pattern_lattices(L)["stripes_i"]  # every 2x2 block ties
