@@ -48,21 +48,27 @@ struct GraphKey {
 
 }  // namespace
 
+// Samples in flight: sample s measures into slot s % PYR_SLOTS (its own set of blocked lattices and popcount cells) and its
+// pyramid runs on that slot's side stream, so up to PYR_SLOTS pyramids overlap each other and the sweeps that follow.
+constexpr int PYR_SLOTS = 4;
+
 struct mcrg_ctx {
     int device = 0, L = 0, W = 0, bits = 0, n_replicas = 0, n_bins = 1, full_levels = 0;
     uint64_t seed = 0;
     uint32_t replica_base = 0;
     cudaStream_t stream = nullptr;   // sweeps (and everything else)
-    cudaStream_t stream2 = nullptr;  // blocked-level pyramid of sample s, overlapped with the sweep of sample s+1
+    cudaStream_t stream2[PYR_SLOTS] = {};  // blocked-level pyramid of sample s (stream2[s % PYR_SLOTS]), overlapped with the sweeps of
+                                           // the next samples and with the pyramids of its neighbours (their accumulation excepted)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_meas[2] = {nullptr, nullptr}, ev_pyr[2] = {nullptr, nullptr};
-    bool pyr_pending[2] = {false, false};
-    int overlap = 1;      // run the pyramid on stream2
+    cudaEvent_t ev_meas[PYR_SLOTS] = {}, ev_pyr[PYR_SLOTS] = {};
+    bool pyr_pending[PYR_SLOTS] = {};
+    int last_tail_slot = -1;  // slot of the most recent k_tail in flight (tails accumulate in sample order)
+    int overlap = 1;      // run the pyramids on the side streams
     int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
     int resident_threads = 0;    // 0: one thread per column walker (kernels.cu: resident_threads); MCRG_RESIDENT_THREADS forces a block size
-    int last_parity = 0;  // which level-1 / popcount buffer the last measurement used
-    size_t level1_words = 0, cnt_cells = 0;
+    int last_parity = 0;  // which slot (blocked lattices / popcount cells) the last measurement used
+    size_t levels_words = 0, cnt_cells = 0;  // words of one set of blocked lattices (PYR_SLOTS sets)
     uint32_t *planes[2] = {nullptr, nullptr};
     int cur = 0;
     uint32_t *levels = nullptr;
@@ -204,7 +210,7 @@ int ensure_stage(mcrg_ctx *c, size_t ints) {
 
 // level-1 lattice and popcount cells are double-buffered by sample parity (see enqueue_sample)
 uint32_t *level_ptr(const mcrg_ctx *c, int lv, int parity) {
-    return c->levels + c->level_off[lv] + (lv == 1 ? (size_t)parity * c->level1_words : 0);
+    return c->levels + (size_t)parity * c->levels_words + c->level_off[lv];
 }
 unsigned long long *cnt_ptr(const mcrg_ctx *c, int parity) { return c->cnt + (size_t)parity * c->cnt_cells; }
 
@@ -274,23 +280,27 @@ void enqueue_updates(mcrg_ctx *c, int n, unsigned long long t_off) {
     else enqueue_sweeps(c, n, t_off);
 }
 
-// make the main stream wait for every pyramid still in flight on stream2 (no-op when nothing is pending)
+// make the main stream wait for every pyramid still in flight on the side streams (no-op when nothing is pending)
 void join_pyramids(mcrg_ctx *c) {
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < PYR_SLOTS; ++p)
         if (c->pyr_pending[p]) {
             cudaStreamWaitEvent(c->stream, c->ev_pyr[p], 0);
             c->pyr_pending[p] = false;
         }
+    c->last_tail_slot = -1;
 }
 
 // enqueue: measure the current configuration at levels 0..n_lv (+ accumulate), fused with the first of
 // `m` sweeps; then the remaining m-1 sweeps.  The blocked-level kernels of sample s (k_level, k_tail) only read
 // the level-1 lattice and the popcount cells written by k_sweep0<MEASURE>; both are double-buffered by `parity`,
-// so they run on stream2 while the main stream already sweeps towards sample s+1.
+// so they run on a side stream while the main stream already sweeps towards sample s+1.  ALL blocked lattices are
+// double-buffered by parity and the two parities have their own side stream, so the pyramid of sample s+1 does not queue
+// behind that of sample s either (a single replica's pyramid is a chain of small, latency-bound launches longer than its
+// sweep); only the accumulation — k_tail adds into the same sums — is ordered: tail(s+1) waits for tail(s).
 void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsigned long long t_off, int parity,
                     cudaEvent_t *probe = nullptr) {
     const bool overlap = c->overlap && probe == nullptr;
-    cudaStream_t s_pyr = overlap ? c->stream2 : c->stream;
+    cudaStream_t s_pyr = overlap ? c->stream2[parity] : c->stream;
     if (c->pyr_pending[parity]) {  // the pyramid of sample s-2 used this buffer pair
         cudaStreamWaitEvent(c->stream, c->ev_pyr[parity], 0);
         c->pyr_pending[parity] = false;
@@ -329,7 +339,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     }
     TailArgs ta;
     ta.in = lv <= n_lv ? level_ptr(c, lv, parity) : nullptr;
-    ta.levels_out = c->levels;
+    ta.levels_out = c->levels + (size_t)parity * c->levels_words;
     ta.ties = c->ties;
     ta.tie_stride = c->tie_stride;
     ta.level_off = c->d_level_off;
@@ -348,11 +358,14 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     ta.bin = bin;
     ta.accumulate = accumulate;
     if (probe) cudaEventRecord(probe[2], c->stream);
+    if (overlap && c->last_tail_slot >= 0 && c->last_tail_slot != parity && c->pyr_pending[c->last_tail_slot])
+        cudaStreamWaitEvent(s_pyr, c->ev_pyr[c->last_tail_slot], 0);  // tails accumulate in sample order
     launch_tail(ta, c->n_replicas, s_pyr);
     if (probe) cudaEventRecord(probe[3], c->stream);
     if (overlap) {
         cudaEventRecord(c->ev_pyr[parity], s_pyr);
         c->pyr_pending[parity] = true;
+        c->last_tail_slot = parity;
     }
     c->last_levels = n_lv;
     c->last_parity = parity;
@@ -474,11 +487,11 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
-        CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));  // small kernels first
+        for (int p = 0; p < PYR_SLOTS; ++p) CK(cudaStreamCreateWithPriority(&c->stream2[p], cudaStreamNonBlocking, prio_hi));  // small kernels first
     }
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < PYR_SLOTS; ++p) {
         CK(cudaEventCreateWithFlags(&c->ev_meas[p], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_pyr[p], cudaEventDisableTiming));
     }
@@ -497,17 +510,17 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
         const int Ln = L >> lv;
         c->level_off[lv] = off;
         size_t words = ((size_t)n_replicas * Ln * nat_words(Ln) + 3) & ~(size_t)3;  // 16-byte aligned for 128-bit loads
-        if (lv == 1) c->level1_words = words;
-        off += (lv == 1 ? 2 : 1) * words;  // level 1 is double-buffered
+        off += words;
     }
-    CK(cudaMalloc(&c->levels, (off + 4) * 4));
-    CK(cudaMemsetAsync(c->levels, 0, (off + 4) * 4, c->stream));
+    c->levels_words = off + 4;  // PYR_SLOTS sets of blocked lattices (see enqueue_sample)
+    CK(cudaMalloc(&c->levels, PYR_SLOTS * c->levels_words * 4));
+    CK(cudaMemsetAsync(c->levels, 0, PYR_SLOTS * c->levels_words * 4, c->stream));
     CK(cudaMalloc(&c->d_level_off, sizeof(c->level_off)));
     CK(cudaMemcpyAsync(c->d_level_off, c->level_off, sizeof(c->level_off), cudaMemcpyHostToDevice, c->stream));
     const size_t n_cnt = (size_t)n_replicas * (MAX_LEVELS + 1) * 4;
     c->cnt_cells = n_cnt;
-    CK(cudaMalloc(&c->cnt, 2 * n_cnt * 8));
-    CK(cudaMemsetAsync(c->cnt, 0, 2 * n_cnt * 8, c->stream));
+    CK(cudaMalloc(&c->cnt, PYR_SLOTS * n_cnt * 8));
+    CK(cudaMemsetAsync(c->cnt, 0, PYR_SLOTS * n_cnt * 8, c->stream));
     CK(cudaMalloc(&c->S_out, n_cnt * 8));
     CK(cudaMemsetAsync(c->S_out, 0, n_cnt * 8, c->stream));
     const size_t n_acc = (size_t)n_replicas * n_bins * N_SLOTS;
@@ -544,7 +557,8 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    for (int p = 0; p < PYR_SLOTS; ++p)
+        if (c->stream2[p]) cudaStreamSynchronize(c->stream2[p]);
     destroy_graphs(c);
     cudaFree(c->planes[0]);
     cudaFree(c->planes[1]);
@@ -575,11 +589,12 @@ int mcrg_ctx_destroy(mcrg_ctx *c) {
     }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < PYR_SLOTS; ++p) {
         if (c->ev_meas[p]) cudaEventDestroy(c->ev_meas[p]);
         if (c->ev_pyr[p]) cudaEventDestroy(c->ev_pyr[p]);
     }
-    if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int p = 0; p < PYR_SLOTS; ++p)
+        if (c->stream2[p]) cudaStreamDestroy(c->stream2[p]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -954,8 +969,8 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
             if (it == c->graphs.end()) {
                 cudaGraph_t g = nullptr;
                 CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s & 1);
-                join_pyramids(c);  // every graph is self-contained: stream2 joins back before the capture ends
+                for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s % PYR_SLOTS);
+                join_pyramids(c);  // every graph is self-contained: the side streams join back before the capture ends
                 launch_advance_t(c->d_t, (unsigned long long)chunk * m, c->stream);
                 cudaError_t e = cudaStreamEndCapture(c->stream, &g);
                 if (e != cudaSuccess) {
@@ -978,7 +993,7 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
                 if (c->update_mode == MCRG_UPDATE_CLUSTER) flips_per_sample = 0;  // cluster updates work in place
                 if ((chunk * flips_per_sample) & 1) c->cur ^= 1;
                 c->last_levels = n_lv;
-                c->last_parity = (chunk - 1) & 1;
+                c->last_parity = (chunk - 1) % PYR_SLOTS;
                 c->measured = true;
             }
             CK(cudaGraphLaunch(it->second, c->stream));
@@ -988,7 +1003,7 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
     }
     const int rest = n_samples - done;
     if (rest > 0) {
-        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s & 1);
+        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s % PYR_SLOTS);
         join_pyramids(c);
         if (m > 0) launch_advance_t(c->d_t, (unsigned long long)rest * m, c->stream);
         c->t_host += (unsigned long long)rest * m;
@@ -1005,7 +1020,7 @@ int mcrg_profile_kernels(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int 
     const int m = sweeps_per_sample;
     std::vector<cudaEvent_t> ev((size_t)n_samples * 5);
     for (auto &e : ev) CK(cudaEventCreate(&e));
-    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, s & 1, &ev[(size_t)s * 5]);
+    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, s % PYR_SLOTS, &ev[(size_t)s * 5]);
     if (m > 0) launch_advance_t(c->d_t, (unsigned long long)n_samples * m, c->stream);
     c->t_host += (unsigned long long)n_samples * m;
     CK(cudaGetLastError());

@@ -406,6 +406,19 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
     else mc_half_sweep_t<0>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
 }
 
+// the strip kernel's dispatcher: the row body with the words per row as a compile-time constant (immediate neighbour offsets)
+// for the named lattice sizes L = 1024, 4096, 16384; any other size takes the general body
+__device__ __forceinline__ void mc_half_sweep_strip(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
+                                                    const McTable *tab, const McQueue &q, uint64_t seed, uint32_t replica,
+                                                    unsigned long long sweep) {
+    if (s.W == 64) mc_half_sweep_t<64>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+#if !defined(MCRG_FEWER_INSTANTIATIONS)
+    else if (s.W == 256) mc_half_sweep_t<256>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+    else if (s.W == 16) mc_half_sweep_t<16>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+#endif
+    else mc_half_sweep_t<0>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+}
+
 // MEASURE phase of a strip whose words are full (bits == 32, L >= 64): the same counts and block words as measure_pair0
 // (tile.cuh), organised like the sweep.  A thread keeps ONE column w and visits the pair rows i0, i0 + di, ... (item
 // index = threadIdx.x + k * blockDim.x, so consecutive items of a thread are 256 output words apart and share a
@@ -587,6 +600,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
         const uint32_t *tie_src = a.ties ? a.ties + (size_t)r * a.tie_stride : nullptr;  // level 1 comes first
         if (a.bits == 32) {  // L >= 64
             if (W == 64) measure_strip_b32<64, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c, tie_src);  // L = 4096
+#if !defined(MCRG_FEWER_INSTANTIATIONS)
+            else if (W == 256) measure_strip_b32<256, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c, tie_src);  // L = 16384
+            else if (W == 16) measure_strip_b32<16, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c, tie_src);    // L = 1024
+#endif
             else measure_strip_b32<0, true>(s, a.H, Rs, lw, y0, lev1, a.seed, replica, t, c, tie_src);
         } else {
             TieCache coins;
@@ -613,7 +630,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
         q.cap = sweep0_queue_cap(rows * W, blockDim.x >> 5);
         const uint32_t anti = a.anti[r];
         for (int h = 0; h < 2 * a.nsw; ++h)
-            mc_half_sweep(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, a.seed, replica,
+            mc_half_sweep_strip(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, a.seed, replica,
                           t + (unsigned long long)(h >> 1));
         uint32_t *dst_r = a.dst + (size_t)r * 2 * L * W;
         if (tma) {  // the R rows of a strip are contiguous in global memory: one bulk store per colour plane
