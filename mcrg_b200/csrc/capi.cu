@@ -408,6 +408,7 @@ void enqueue_resident_launch(mcrg_ctx *c, bool measure, int n_samples, int m, in
     a.W = c->W;
     a.bits = c->bits;
     a.n_samples = n_samples;
+    a.n_replicas = c->n_replicas;
     a.m = m;
     a.n_levels = n_lv;
     a.accumulate = accumulate;

@@ -1069,6 +1069,248 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
     }
 }
 
+// ---- resident kernel for the smallest lattices: several replicas per warp ----------------------------------------------
+// L <= 32: a replica has one word per row and colour and L/2 column walkers (two rows each per half-sweep), so a one-warp CTA
+// of k_resident keeps L/2 of its 32 lanes busy (4 at L = 8, BASELINE config 1).  Here a warp takes 64/L replicas at once:
+// lane = (replica within the warp, walker), every lane runs its own replica's Philox stream with its own thresholds, the
+// warp collectives become segment-wide (shuffles of width L/2), and the few words whose lanes are still undecided after the
+// first calls are finished in place by the lane that owns them (no queue: a warp has at most 32 words in flight).  Same
+// specification, same results as k_resident — the update is the scalar form metropolis_flip_mask itself.
+struct MultiLayout {
+    int planes_off, bufA_off, S_off, red_off, tab_off, per_replica, dec_off, total_words, sdim;
+};
+MCRG_HD MultiLayout multi_layout(int L, int n_levels) {
+    MultiLayout o;
+    const int rpw = L >= 2 ? 64 / L : 32;                   // replicas per warp
+    const int n_live = 6 + (NOP + NOP * NOP) * (n_levels + 1) + 2 * NOP * NOP * n_levels;
+    o.sdim = (n_levels + 1) * 4 + 4;                        // the sums of a sample + the four pseudo-entries (acc_slot_decode)
+    o.planes_off = 0;                                       // [colour][L + 2] words
+    o.bufA_off = 2 * (L + 2);                               // level-1 lattice, L/2 words (at least 1)
+    o.S_off = o.bufA_off + (L / 2 > 0 ? L / 2 : 1);         // int [sdim]: |S| <= 4 L^2 <= 4096 here
+    o.red_off = o.S_off + o.sdim;                           // unsigned [(n_levels + 1) * 4]
+    o.tab_off = (o.red_off + (n_levels + 1) * 4 + 3) & ~3;  // McTable (64 words), 16-byte aligned
+    o.per_replica = o.tab_off + 64;
+    o.dec_off = o.per_replica * rpw;                        // int2 [n_live], shared by the replicas of the warp
+    o.total_words = o.dec_off + 2 * n_live;
+    return o;
+}
+
+// accumulator slots a lane of k_resident_multi owns at most: ceil(n_live / (L/2)) over L = 2 .. 32
+constexpr int MULTI_KMAX = 24;
+
+// sum over the lanes of a segment of width G (a power of two), result in every lane of the segment
+__device__ __forceinline__ uint32_t seg_sum(uint32_t v, int G) {
+    for (int d = 1; d < G; d <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+template <bool MEASURE>
+__global__ void __launch_bounds__(32, 16) k_resident_multi(const __grid_constant__ ResidentArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int L = a.L, G = L >= 2 ? (L / 2 > 0 ? L / 2 : 1) : 1, rpw = 32 / G;
+    const int lane = threadIdx.x, gi = lane / G, li = lane - gi * G;
+    const int r = blockIdx.x * rpw + gi;
+    const bool live = r < a.n_replicas;
+    const MultiLayout lay = multi_layout(L, a.n_levels);
+    const int rows = L + 2, n_lv = a.n_levels;
+    uint32_t *mine = smem + gi * lay.per_replica;
+    Strip0 s;
+    s.base = mine + lay.planes_off;
+    s.rows = rows;
+    s.W = 1;
+    s.bits = a.bits;
+    s.mask = valid_mask(a.bits);
+    s.L = L;
+    s.y_first = L - 1;
+    uint32_t *bufA = mine + lay.bufA_off;
+    int *S_sh = reinterpret_cast<int *>(mine + lay.S_off);
+    unsigned int *red = mine + lay.red_off;
+    McTable *tab = reinterpret_cast<McTable *>(mine + lay.tab_off);
+    // this lane's accumulator slots li, li + G, ..: 64-bit sums in registers for the whole launch (products <= 2^24, the host
+    // layer splits runs at 2^22 samples), one IMAD.WIDE per slot and sample
+    long long acc[MULTI_KMAX];
+#pragma unroll
+    for (int j = 0; j < MULTI_KMAX; ++j) acc[j] = 0ll;
+    int2 *dec = reinterpret_cast<int2 *>(smem + lay.dec_off);
+    const int n_live = acc_live_slots(n_lv), s_one = (n_lv + 1) * 4;
+    const uint32_t replica = a.replica_base + (uint32_t)(live ? r : 0);
+    const unsigned long long t0 = *a.d_t + a.t_off;
+    const uint32_t T4 = live ? a.T4[r] : 0u, T8 = live ? a.T8[r] : 0u, anti = live ? a.anti[r] : 0u;
+    uint32_t *gl = a.planes + (size_t)(live ? r : 0) * 2 * L;
+    for (int k = li; k < 64; k += G) tab->tm[k >> 1][k & 1] = ((((k & 1) ? T8 : T4) >> (31 - (k >> 1))) & 1u) ? 0xFFFFFFFFu : 0u;
+
+    if (live)
+        for (int idx = li; idx < 2 * rows; idx += G) {  // both planes with their periodic halo rows
+            const int c = idx / rows, lr = idx - c * rows;
+            s.base[idx] = gl[c * L + ((L - 1 + lr) & (L - 1))];
+        }
+    if (MEASURE) {
+        for (int k = lane; k < n_live; k += 32) {  // slot decoding, once per launch, shared by the warp's replicas
+            int slot, ia, ib;
+            acc_slot_decode(k, n_lv, slot, ia, ib);
+            if (ia >= X_ONE) ia = s_one + (ia - X_ONE);
+            if (ib >= X_ONE) ib = s_one + (ib - X_ONE);
+            dec[k] = make_int2(slot, ia | (ib << 8));
+        }
+        if (li == 0) S_sh[s_one] = 1;  // X_ONE
+    }
+    __syncwarp();
+
+    for (int smp = 0; smp < a.n_samples; ++smp) {
+        const unsigned long long t = t0 + (unsigned long long)smp * a.m;
+        if (MEASURE) {
+            // level 0: one row pair per lane (L >= 4; the 2 x 2 lattice has a single pair), block to level 1
+            Counts c = {0u, 0u, 0u, 0u};
+            if (live && 2 * li < L) {
+                uint32_t maj, tie;
+                measure_pair0(s, 1 + 2 * li, 0, c, maj, tie);
+                if (tie) maj |= tie & tie_word(a.seed, (uint32_t)li, replica, t, 1);
+                bufA[li] = maj;
+            }
+            const uint32_t c0 = seg_sum(c.anti_nn, G), c1 = seg_sum(c.anti_nnn, G), c2 = seg_sum(c.odd_plaq, G), c3 = seg_sum(c.up, G);
+            if (li == 0) {
+                red[0] = c0;
+                red[1] = c1;
+                red[2] = c2;
+                red[3] = c3;
+            }
+            __syncwarp();
+            // levels 1 .. n_lv: one row per lane of the segment (pyramid_tail_warp, segment-wide)
+            if (n_lv >= 1) {
+                int Ln = L >> 1;
+                uint32_t row = (live && li < Ln) ? bufA[li] : 0u;
+                uint32_t coin = 0u;
+                {
+                    int base = 0, my_lv = -1, my_q = 0;
+                    for (int lv = 1, n = Ln >> 1; lv < n_lv; ++lv, n >>= 1) {
+                        if (li >= base && li < base + n) {
+                            my_lv = lv + 1;
+                            my_q = li - base;
+                        }
+                        base += n;
+                    }
+                    if (my_lv >= 0) coin = tie_word(a.seed, (uint32_t)my_q, replica, t, my_lv);
+                }
+                int coin_base = 0;
+                for (int lv = 1; lv <= n_lv; ++lv, Ln >>= 1) {
+                    const int bits = Ln;
+                    const uint32_t mask = valid_mask(bits);
+                    const int below = (li + 1 >= Ln) ? 0 : li + 1;
+                    const uint32_t r0 = row, r1 = __shfl_sync(0xFFFFFFFFu, row, below, G);
+                    uint32_t q0 = 0u, q1 = 0u, q2 = 0u, q3 = 0u;
+                    if (li < Ln) {
+                        const uint32_t r0u = shift_up_index(r0, r0, bits, mask), r1u = shift_up_index(r1, r1, bits, mask);
+                        const uint32_t r1d = shift_down_index(r1, r1, bits, mask);
+                        q0 = popc32(r0 ^ r0u) + popc32(r0 ^ r1);
+                        q1 = popc32(r0 ^ r1u) + popc32(r0 ^ r1d);
+                        q2 = popc32(r0 ^ r0u ^ r1 ^ r1u);
+                        q3 = popc32(r0);
+                    }
+                    q0 = seg_sum(q0, G);
+                    q1 = seg_sum(q1, G);
+                    q2 = seg_sum(q2, G);
+                    q3 = seg_sum(q3, G);
+                    if (li == 0) {
+                        red[lv * 4 + 0] = q0;
+                        red[lv * 4 + 1] = q1;
+                        red[lv * 4 + 2] = q2;
+                        red[lv * 4 + 3] = q3;
+                    }
+                    if (lv < n_lv) {
+                        const int Lb = Ln >> 1;
+                        const uint32_t cw = __shfl_sync(0xFFFFFFFFu, coin, (coin_base + (li >> 1)) & (G - 1), G);
+                        coin_base += Lb;
+                        uint32_t o = 0u;
+                        if (li < Ln && !(li & 1)) {  // rows (li, li + 1) -> block row li / 2
+                            uint32_t m, tie;
+                            majority4(r0, r0 >> 1, r1, r1 >> 1, m, tie);
+                            o = compress_even(m) | (compress_even(tie) & cw);
+                        }
+                        row = __shfl_sync(0xFFFFFFFFu, o, (2 * li) & (G - 1), G);
+                        if (li >= Lb) row = 0u;
+                    }
+                }
+            }
+            __syncwarp();
+            for (int lv = li; lv <= n_lv; lv += G) {
+                long long S[4];
+                counts_to_S((long long)(L >> lv), red[lv * 4 + 0], red[lv * 4 + 1], red[lv * 4 + 2], red[lv * 4 + 3], S);
+                for (int k = 0; k < 4; ++k) S_sh[lv * 4 + k] = (int)S[k];
+                if (lv == 0) {
+                    S_sh[s_one + 1] = (int)(S[3] < 0 ? -S[3] : S[3]);                            // X_ABSM
+                    S_sh[s_one + 2] = (int)((S[3] * S[3]) >> M4_SPLIT_BITS);                     // X_M2H
+                    S_sh[s_one + 3] = (int)((S[3] * S[3]) & ((1ll << M4_SPLIT_BITS) - 1));      // X_M2L
+                }
+            }
+            __syncwarp();
+            if (a.accumulate) {
+#pragma unroll
+                for (int j = 0; j < MULTI_KMAX; ++j) {
+                    const int k = li + j * G;
+                    if (k < n_live) {
+                        const int e = dec[k].y;
+                        acc[j] += (long long)S_sh[e & 255] * (long long)S_sh[e >> 8];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        for (int h = 0; h < 2 * a.m; ++h) {
+            const int c = h & 1, o = 1 - c;
+            uint32_t *pc = s.base + c * rows;
+            const uint32_t *po = s.base + o * rows;
+            const unsigned long long sweep = t + (unsigned long long)(h >> 1);
+            const uint32_t c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
+            const McPhiloxHead head = mc_philox_head(a.seed, replica, (uint32_t)sweep);
+            if (live)
+                for (int lr = 1 + 2 * li; lr < 1 + 2 * li + 2 && lr <= L; ++lr) {  // two rows per lane (both rows of the 2 x 2 lattice)
+                    const int y = lr - 1;
+                    const uint32_t tw = pc[lr], n0 = po[lr];
+                    const uint32_t n1 = ((y + c) & 1) ? shift_up_index(n0, n0, s.bits, s.mask) : shift_down_index(n0, n0, s.bits, s.mask);
+                    const uint32_t word_id = (uint32_t)(c * L + y);
+                    // the fast forms of mcfast.cuh (same decisions as metropolis_flip_mask): two calls and eight planes at once,
+                    // what is left — rarely anything with at most 16 sites per word — is finished in place
+                    uint32_t ge2, sel;
+                    mc_neighbour_count(tw ^ po[lr - 1] ^ anti, tw ^ po[lr + 1] ^ anti, tw ^ n0 ^ anti, tw ^ n1 ^ anti, ge2, sel);
+                    uint32_t eq = ~ge2 & s.mask, lt = 0u;
+                    U4 r0, r1;
+                    mc_philox_pair(head, a.seed, word_id, c3_base, r0, r1);
+                    mc_compare4(r0, tab, 0, sel, eq, lt);
+                    mc_compare4(r1, tab, 4, sel, eq, lt);
+                    if (eq != 0u) lt |= mc_finish(eq, sel, 2, tab, head, a.seed, word_id, c3_base);
+                    pc[lr] = tw ^ ((ge2 & s.mask) | lt);
+                }
+            __syncwarp();
+            if (live && li == 0) {  // refresh this colour's periodic halo rows
+                pc[0] = pc[L];
+                pc[L + 1] = pc[1];
+            }
+            __syncwarp();
+        }
+    }
+
+    if (live && a.m > 0)
+        for (int idx = li; idx < 2 * L; idx += G) {
+            const int c = idx / L, y = idx - c * L;
+            gl[c * L + y] = s.base[c * rows + 1 + y];
+        }
+    if (MEASURE && live) {
+        for (int lv = li; lv <= n_lv; lv += G)
+            for (int k = 0; k < 4; ++k) a.S_out[((size_t)r * (MAX_LEVELS + 1) + lv) * 4 + k] = S_sh[lv * 4 + k];
+        if (a.accumulate) {
+            const size_t base = ((size_t)r * a.n_bins + a.bin) * N_SLOTS;
+#pragma unroll
+            for (int j = 0; j < MULTI_KMAX; ++j) {
+                const int k = li + j * G;
+                if (k < n_live) {
+                    const int slot = dec[k].x;
+                    add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], (__int128)acc[j]);
+                }
+            }
+        }
+    }
+}
+
 int g_max_smem = -1;
 
 }  // namespace
@@ -1138,6 +1380,15 @@ int resident_threads(int L, int forced) {
 
 void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int forced_threads, cudaStream_t st) {
     sweep0_max_smem();
+    if (a.L <= 32 && forced_threads == 0) {  // several replicas per warp (k_resident_multi)
+        const int rpw = 64 / a.L;
+        const size_t smem = (size_t)multi_layout(a.L, a.n_levels).total_words * sizeof(uint32_t);
+        ResidentArgs b = a;
+        b.n_replicas = n_replicas;
+        if (measure) k_resident_multi<true><<<(n_replicas + rpw - 1) / rpw, 32, smem, st>>>(b);
+        else k_resident_multi<false><<<(n_replicas + rpw - 1) / rpw, 32, smem, st>>>(b);
+        return;
+    }
     const int threads = resident_threads(a.L, forced_threads);
     const size_t smem = (size_t)resident_layout(a.L, threads, a.n_levels).total_words * sizeof(uint32_t);
     if (threads == 32 && l0_words(a.L) == 1) {  // one-warp CTAs of one-word rows (L <= 64), 28 per SM

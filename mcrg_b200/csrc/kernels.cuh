@@ -100,6 +100,7 @@ struct ResidentArgs {
     uint32_t replica_base;
     int L, W, bits;
     int n_samples, m;          // n_samples x { [measure], m sweeps }
+    int n_replicas;            // (k_resident_multi: several replicas per CTA)
     int n_levels, accumulate, n_bins, bin;
     unsigned long long *acc_lo;
     long long *acc_hi;
