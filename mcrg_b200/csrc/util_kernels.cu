@@ -98,21 +98,27 @@ __global__ void k_unpackN(const uint32_t *lev, int32_t *spins, int Ln, int Wn, s
     if (x < Ln) spins[ry * (size_t)Ln + x] = ((word >> lane) & 1u) ? 1 : -1;
 }
 
-// totals over (replica, bin) of every slot, as four 32-bit limbs in int64 (top limb signed)
-__global__ void k_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out) {
+// totals over (replica, bin) of every slot, as four 32-bit limbs in int64 (top limb signed).  blockIdx.y takes a chunk of the
+// (replica, bin) range, sums it exactly in 128 bits and adds its four limbs to `out` (zeroed by the launcher) with 64-bit
+// atomics: limbs may then exceed 32 bits, which the consumers allow for anyway (they are summed over ranks next) — any
+// order of the additions gives the same integers.  (One thread per slot walking all replicas took 12 ms for the 65535 replicas
+// of BASELINE config 1.)
+__global__ void k_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, int chunk, long long *out) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= N_SLOTS) return;
+    const int k0 = blockIdx.y * chunk, k1 = min(n_rb, k0 + chunk);
     __int128 tot = 0;
-    for (int k = 0; k < n_rb; ++k) {
+    for (int k = k0; k < k1; ++k) {
         const size_t i = (size_t)k * N_SLOTS + slot;
         tot += ((__int128)hi[i] << 64) | (__int128)lo[i];
     }
     const unsigned long long tl = (unsigned long long)tot;
     const long long th = (long long)(tot >> 64);
-    out[4 * slot + 0] = (long long)(tl & 0xFFFFFFFFull);
-    out[4 * slot + 1] = (long long)(tl >> 32);
-    out[4 * slot + 2] = (long long)((unsigned long long)th & 0xFFFFFFFFull);
-    out[4 * slot + 3] = th >> 32;
+    unsigned long long *o = reinterpret_cast<unsigned long long *>(out) + 4 * slot;
+    atomicAdd(o + 0, tl & 0xFFFFFFFFull);
+    atomicAdd(o + 1, tl >> 32);
+    atomicAdd(o + 2, (unsigned long long)th & 0xFFFFFFFFull);
+    atomicAdd(o + 3, (unsigned long long)(th >> 32));  // two's complement: adds the signed top limb
 }
 
 // Instruction-throughput probe for the roofline note of bench.py: the arithmetic core of the Metropolis row body and
@@ -168,7 +174,12 @@ int probe_philox_rate(cudaStream_t st, double *calls_per_s) {
 }
 
 void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st) {
-    k_total_limbs<<<(N_SLOTS + 127) / 128, 128, 0, st>>>(lo, hi, n_rb, out);
+    int n_chunks = n_rb < 512 ? n_rb : 512;
+    if (n_chunks < 1) n_chunks = 1;
+    const int chunk = (n_rb + n_chunks - 1) / n_chunks;
+    n_chunks = (n_rb + chunk - 1) / chunk > 0 ? (n_rb + chunk - 1) / chunk : 1;
+    cudaMemsetAsync(out, 0, sizeof(long long) * 4 * N_SLOTS, st);
+    k_total_limbs<<<dim3((N_SLOTS + 127) / 128, n_chunks), 128, 0, st>>>(lo, hi, n_rb, chunk, out);
 }
 
 void launch_advance_t(unsigned long long *d_t, unsigned long long by, cudaStream_t st) { k_advance_t<<<1, 1, 0, st>>>(d_t, by); }
