@@ -92,3 +92,22 @@ def test_dropin_driver_on_two_devices_prints_the_same_result(tmp_path):
         assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
         outs.append(re.findall(r"RESULT level (\d+) lambda (\S+) err (\S+) nu (\S+)", out.stdout))
     assert len(outs[0]) == 4 and outs[0] == outs[1]
+
+
+def test_dropin_totals_beyond_64_bits_on_two_devices(tmp_path):
+    """N = 4096 with 64 chains x 400 samples: the slot totals (sum S_nn^2 ~ 1.4e15 per sample) pass 2^64, where a running
+    long-double sum of the per-chain values no longer equals the exact all-reduced total.  The drop-in compares the two in exact
+    integers, so the two-device run must go through (round 1 threw "all-reduced totals differ") and print what one device prints."""
+    import mcrg_b200
+
+    if mcrg_b200.capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    outs = []
+    for n_dev in ("1", "2"):
+        d = tmp_path / n_dev
+        d.mkdir()
+        env = dict(os.environ, MCRG_REPLICAS="64", MCRG_SEED="5", MCRG_QUIET="1", MCRG_DEVICES=n_dev, MCRG_UPDATE="metropolis")
+        out = subprocess.run([APP, "exponent", "4096", repr(KC), "50", str(64 * 400)], cwd=d, env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        outs.append(re.findall(r"RESULT level (\d+) lambda (\S+) err (\S+) nu (\S+)", out.stdout))
+    assert len(outs[0]) == 11 and outs[0] == outs[1]
