@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
     limbs = torch.zeros(lay.n_slots * 4, dtype=torch.int64, device="cuda")
     n_lv = capi.levels_full(L) if max_lv < 0 else min(max_lv, capi.levels_full(L))
     resident = L <= 512 and not args.strip_rows
-    n_level_kernels = sum(1 for lv in range(1, n_lv + 1) if (L >> lv) > 256)
+    n_level_kernels = sum(1 for lv in range(1, n_lv + 1) if (L >> lv) > (512 if n_loc >= 16 else 256))  # capi.cu: tail_start_size
     # strips: per sample k_sweep0<measure>, k_level per large level, k_tail, further sweep launches; per step the sweep-counter
     # update(s) (one per 16-sample graph + one for the rest) and the limb-total kernel.  resident: one launch per block.
     extra_sweeps = 0 if m <= 1 else -(-(m - 1) // max(1, args.fuse_sweeps))

@@ -129,6 +129,16 @@ void mcrg_ctx_set_comm(mcrg_ctx *c, void *comm, void *limbs) {
 
 namespace {
 
+// Largest blocked lattice that k_tail (one CTA per replica) takes over from k_level (strips): 512^2 when the batch has a CTA for
+// every few SMs — one launch less per sample —, 256^2 for a handful of replicas, whose pyramid is a latency-bound chain already.
+int tail_start_size(const mcrg_ctx *c) {
+    if (const char *e = getenv("MCRG_TAIL_START")) {
+        const int v = atoi(e);
+        if (v == 256 || v == 512) return v;
+    }
+    return c->n_replicas >= 16 ? TAIL_MAX_L : 256;
+}
+
 // Row steps a half-sweep over `nrows` rows costs a CTA of `threads` threads (the row distribution of mc_half_sweep_t): a thread
 // owns one column, the threads / W row groups take whole row pairs (W >= 32) or equal even chunks (W < 32).
 int half_sweep_steps(int nrows, int W, int threads) {
@@ -192,7 +202,8 @@ int choose_R(mcrg_ctx *c, int H) {
 int choose_Rn(int Ln) {
     const int Wn = nat_words(Ln);
     int R = 4096 / Wn;
-    if (R > 64) R = 64;
+    static const int cap = [] { const char *e = getenv("MCRG_LEVEL_ROWS"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 256 && (v & (v - 1)) == 0) ? v : 64; }();
+    if (R > cap) R = cap;
     if (R < 2) R = 2;
     if (R > Ln) R = Ln;
     return R;
@@ -318,7 +329,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
         cudaStreamWaitEvent(s_pyr, c->ev_meas[parity], 0);
     }
     int lv = 1;
-    while (lv <= n_lv && (c->L >> lv) > TAIL_MAX_L) {
+    while (lv <= n_lv && (c->L >> lv) > tail_start_size(c)) {
         LevelArgs la;
         la.in = level_ptr(c, lv, parity);
         la.out = lv < n_lv ? level_ptr(c, lv + 1, parity) : nullptr;

@@ -13,7 +13,9 @@ __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }  // v a po
 
 constexpr int MAX_LEVELS = 15;          // L <= 2^15; levels 0..14 at most
 constexpr int NOP = 3;                  // even operators: nn, nnn, plaquette
-constexpr int TAIL_MAX_L = 256;         // blocked lattices up to this size finish inside one CTA's shared memory
+constexpr int TAIL_MAX_L = 512;         // blocked lattices up to this size CAN finish inside one CTA's shared memory (k_tail's buffers);
+                                        // the host starts the tail at 512^2 when there are enough replicas to fill the SMs with
+                                        // one CTA each, else at 256^2 (capi.cu: tail_start_size)
 constexpr int SWEEP_THREADS = 256;
 // capacity of a warp's "still undecided after 8 bit planes" queue for a strip with `words` words per colour
 // (expected fill: ~10 % of the words)
