@@ -1,7 +1,7 @@
-# A/B of library builds under gpurun_ab/lib*.so (same sources, different compile-time choices): rates on C3 / C4 / C5
+# A/B of library builds under gpurun_ab/lib*.so (same sources, different compile-time choices): rates per config
 for lib in gpurun_ab/lib*.so; do
   echo "=== $lib"
-  MCRG_LIB=$PWD/$lib python profiles/configs_bench.py --only "C4 L=4096 x 40" 2>&1 | tail -1
+  MCRG_LIB=$PWD/$lib python profiles/configs_bench.py --only "x 40" 2>&1 | tail -1
   MCRG_LIB=$PWD/$lib python profiles/configs_bench.py --only "C3" 2>&1 | tail -1
   MCRG_LIB=$PWD/$lib python profiles/configs_bench.py --only "C5" 2>&1 | tail -1
   MCRG_LIB=$PWD/$lib python profiles/configs_bench.py --only "C2" 2>&1 | tail -1
