@@ -470,6 +470,42 @@ def run_ours(args, rank, world, local_rank):
         host_roofline = attempts_per_step / max(t_host, block_ms * 1e-3) / 1e9
         del bufs, pk
 
+    # the other named configurations, device-resident, a few steps each (same timing rules: warm-up, barrier + max over ranks,
+    # CUDA events on the context's stream) so that one default run shows every BASELINE shape; `--config Cn` gives the full line
+    others = {}
+    if args.config == "C4" and not args.no_other_configs:
+        for name in ("C1", "C2", "C3", "C5"):
+            oL, oKs, oper, olv, oS, odesc = CONFIGS[name]
+            on = len(oKs) * oper
+            octx = mcrg_b200.Context(oL, on, seed=12345, device=local_rank, replica_base=rank * on, n_bins=1)
+            octx.set_couplings(np.repeat(oKs, oper))
+            octx.init_hot()
+            octx.sweep(10)
+            ostream = torch.cuda.ExternalStream(octx.stream_handle, device=torch.device("cuda", local_rank))
+            with torch.cuda.stream(ostream):
+                def oblock():
+                    octx.run(oS, 1, olv, 0)
+                    octx.total_limbs_to_device(limbs.data_ptr())
+                    if world > 1:
+                        dist.all_reduce(limbs)
+                for _ in range(3):
+                    oblock()
+                barrier()
+                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_steps = 5
+                o0.record(ostream)
+                for _ in range(n_steps):
+                    oblock()
+                o1.record(ostream)
+                barrier()
+                oms = max_over_ranks(o0.elapsed_time(o1))
+            others[name] = {"workload": odesc, "value": world * on * oL * oL * oS * n_steps / (oms * 1e-3) / 1e9, "unit": UNIT,
+                            "ms_per_step": oms / n_steps, "steps": n_steps, "warmup": 3, "replicas_per_gpu": on, "samples_per_step": oS,
+                            "levels": (capi.levels_full(oL) if olv < 0 else min(olv, capi.levels_full(oL))) + 1}
+            del o0, o1
+            torch.cuda.synchronize()
+            octx.close()
+
     peak, peak_src = measured_peak()
     sites = n_loc * L * L
     if prof is not None:
@@ -518,6 +554,7 @@ def run_ours(args, rank, world, local_rank):
                                   "e2e_over_roofline": e2e_value / host_roofline}},
         "gpu_launches": launches_per_step * args.steps,
         "other_schedules_per_gpu": {"unit": UNIT, "sweep_only": other["sweep_only"], "one_measurement_per_16_sweeps": other["m16"]},
+        "other_configs": others,
         "roofline": {"bound": "hbm", "kernel": dom_name,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
@@ -570,6 +607,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of every end-to-end variant (default: --steps)")
     ap.add_argument("--ref-samples", type=int, default=0, help="reference samples per process per step (0 = about a second of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short device-resident runs of C1, C2, C3, C5 in the default line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
