@@ -62,7 +62,6 @@ struct mcrg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_meas[PYR_SLOTS] = {}, ev_pyr[PYR_SLOTS] = {};
     bool pyr_pending[PYR_SLOTS] = {};
-    int last_tail_slot = -1;  // slot of the most recent k_tail in flight (tails accumulate in sample order)
     int overlap = 1;      // run the pyramids on the side streams
     int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
@@ -298,7 +297,6 @@ void join_pyramids(mcrg_ctx *c) {
             cudaStreamWaitEvent(c->stream, c->ev_pyr[p], 0);
             c->pyr_pending[p] = false;
         }
-    c->last_tail_slot = -1;
 }
 
 // enqueue: measure the current configuration at levels 0..n_lv (+ accumulate), fused with the first of
@@ -307,7 +305,7 @@ void join_pyramids(mcrg_ctx *c) {
 // so they run on a side stream while the main stream already sweeps towards sample s+1.  ALL blocked lattices are
 // double-buffered by parity and the two parities have their own side stream, so the pyramid of sample s+1 does not queue
 // behind that of sample s either (a single replica's pyramid is a chain of small, latency-bound launches longer than its
-// sweep); only the accumulation — k_tail adds into the same sums — is ordered: tail(s+1) waits for tail(s).
+// sweep); the accumulation needs no order: k_tail adds into the 128-bit sums with atomics (exact in any interleaving).
 void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsigned long long t_off, int parity,
                     cudaEvent_t *probe = nullptr) {
     const bool overlap = c->overlap && probe == nullptr;
@@ -369,14 +367,11 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     ta.bin = bin;
     ta.accumulate = accumulate;
     if (probe) cudaEventRecord(probe[2], c->stream);
-    if (overlap && c->last_tail_slot >= 0 && c->last_tail_slot != parity && c->pyr_pending[c->last_tail_slot])
-        cudaStreamWaitEvent(s_pyr, c->ev_pyr[c->last_tail_slot], 0);  // tails accumulate in sample order
     launch_tail(ta, c->n_replicas, s_pyr);
     if (probe) cudaEventRecord(probe[3], c->stream);
     if (overlap) {
         cudaEventRecord(c->ev_pyr[parity], s_pyr);
         c->pyr_pending[parity] = true;
-        c->last_tail_slot = parity;
     }
     c->last_levels = n_lv;
     c->last_parity = parity;

@@ -817,6 +817,17 @@ __device__ __forceinline__ void add128(unsigned long long *lo, long long *hi, __
     *hi = *hi + vhi + (nl < old ? 1 : 0);
 }
 
+// The same with atomics, for sums that several kernels in flight add to (the k_tail launches of up to four samples): every
+// addition to the low word sees a consistent old value, so the carries it hands to the high word add up to exactly the number of
+// wraps — the final 128-bit sum is exact whatever the interleaving; it is read only after all of them are done.
+__device__ __forceinline__ void atomic_add128(unsigned long long *lo, long long *hi, __int128 v) {
+    const unsigned long long vlo = (unsigned long long)v;
+    const long long vhi = (long long)(v >> 64);
+    const unsigned long long old = atomicAdd(lo, vlo);
+    const long long carry = (old + vlo) < old ? 1 : 0;
+    if (vhi + carry != 0) atomicAdd(reinterpret_cast<unsigned long long *>(hi), (unsigned long long)(vhi + carry));
+}
+
 // The accumulator slots that are live for a pyramid of n_levels blocking levels, in a compact order:
 // k -> (slot index in the public layout, this sample's contribution).  S_sh[lv*4 + {nn, nnn, plaq, sum}].
 // mcrg.cpp:86-97 with the column-major flatten of definitions.cpp:9-19 (index b*NOP+a holds X_a * Y_b).
@@ -926,7 +937,7 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
         int slot;
         __int128 v;
         acc_slot_value(k, a.n_levels, S_sh, slot, v);
-        add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], v);
+        atomic_add128(&a.acc_lo[base + slot], &a.acc_hi[base + slot], v);
     }
 }
 
