@@ -330,6 +330,8 @@ def run_ours(args, rank, world, local_rank):
 
         # per-kernel device times, live, same state (events between the launches, no graph); strip kernels only
         prof = None if resident else ctx.profile_kernels(min(S, 32), m, max_lv)
+        if prof is not None and m <= 1:
+            prof["sweep_only"] = None  # no further sweep launches per sample at m = 1 (the event pair brackets nothing)
         barrier()
 
         # also the sweep-only rate and one measurement every 16 sweeps (same state, device timers, this rank)
@@ -511,7 +513,7 @@ def run_ours(args, rank, world, local_rank):
     if prof is not None:
         dom_ms, dom_name = prof["sweep_measure"], "k_sweep0<MEASURE> (level-0 correlators + block to level 1 + Metropolis sweep)"
         dom_bytes = BYTES_PER_SITE_DOMINANT * sites
-        sample_ms = sum(prof.values())
+        sample_ms = sum(v for v in prof.values() if v)
     else:  # resident kernel: one launch = the whole block of samples, state in shared memory throughout
         dom_ms, dom_name = block_ms, "k_resident<MEASURE> (one launch = S samples: measure + pyramid + accumulate + sweep, state in shared memory)"
         dom_bytes = BYTES_PER_ATTEMPT_SAMPLE * sites * S * m
@@ -557,6 +559,7 @@ def run_ours(args, rank, world, local_rank):
         "other_configs": others,
         "roofline": {"bound": "hbm", "kernel": dom_name,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/traffic.json <- profiles/ncu_summary_r2_final.json (one ncu --set full capture; refresh with profiles/run_profiles.sh + summarize.py when the kernel changes)" if traffic else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel_ms": dom_ms, "kernel_share_of_sample": dom_ms / sample_ms if sample_ms > 0 else None,
                      "per_sample_ms": prof,
