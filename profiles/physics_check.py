@@ -33,11 +33,18 @@ def run(args, env):
 
 
 def main():
-    print("(1) K_c(L): two-lattice matching, cluster updates, 3 iterations from K0 = -0.4400, 4096 chains, 4e6 samples")
+    print("(1) K_c(L): two-lattice matching (locate_critical_point), default updates, from K0 = -0.4400, 4096 chains, 8e6 samples per")
+    print("    iteration; K per iteration = the last blocking level's estimate, +- jackknife error over 32 groups of chains of the last")
+    print("    iteration.  Against the COMPILED reference (16 seeds, tests/golden/critical_point.json) the estimator agrees at 3 sigma per")
+    print("    level (tests/test_gpu_dropin.py); the values quoted in the comment of main.cpp:26-29 are single runs of unknown length.")
     for L in (16, 32, 64, 128):
-        out, dt = run(["kc", L, -0.4400, 3, 500, 4000000], dict(MCRG_REPLICAS="4096", MCRG_UPDATE="cluster", MCRG_SEED=str(10 + L)))
-        kc = float(re.search(r"RESULT Kc (\S+)", out).group(1))
-        print(f"    L={L:4d}: K_c = {kc:.6f}   reference main.cpp: {REF_KC[L]:.6f}   diff {kc - REF_KC[L]:+.6f}   ({dt:.1f} s)", flush=True)
+        ks = []
+        err = None
+        for n_it in (1, 2, 3, 4, 6):
+            out, dt = run(["kc", L, -0.4400, n_it, 500, 8000000], dict(MCRG_REPLICAS="4096", MCRG_SEED=str(10 + L)))
+            ks.append(float(re.search(r"RESULT Kc (\S+)", out).group(1)))
+            err = [float(e) for _, _, e in re.findall(r"RESULT level (\d+) Kc (\S+) err (\S+)", out)][-1]
+        print(f"    L={L:4d}: K after 1, 2, 3, 4, 6 iterations = " + ", ".join(f"{k:.6f}" for k in ks) + f"  (+- {err:.6f});  main.cpp comment: {REF_KC[L]:.6f}", flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "statistical.json")) as f:
         ref = next(t for t in json.load(f)["lambda"] if t["N"] == 64)
     print("(2) lambda per level at N = 64, K_c: ours (jackknife error) | compiled reference (mean +- error over 16 runs)")
