@@ -115,6 +115,17 @@ struct DeviceBatch {
     DeviceBatch &operator=(const DeviceBatch &) = delete;
 };
 
+// Metropolis chosen explicitly on a large lattice: one sweep is not one Wolff update there (tau ~ N^2.17 sweeps at K_c), so an
+// equilibration of `n_updates` updates from a hot start may leave the chains unequilibrated — say so once per call
+static void warn_if_metropolis_is_short(int N, long n_updates) {
+    if (DeviceBatch::use_cluster(N) || settings().quiet || N < 64) return;
+    const double tau = std::pow((double)N, 2.17);
+    if ((double)n_updates * settings().sweeps_per_update < tau)
+        fprintf(stderr, "mcrg_b200: note: %ld Metropolis update(s) x %d sweep(s) on N = %d is short of the relaxation time (~N^2.17 = %.0f sweeps at K_c); "
+                        "MCRG_UPDATE=cluster (the default for N >= 32) or a larger MCRG_SWEEPS_PER_UPDATE avoids biased, autocorrelated samples\n",
+                n_updates, settings().sweeps_per_update, N, tau);
+}
+
 // Lattice objects get Philox replica ids above the range the drivers use for their batches
 static std::atomic<std::uint32_t> g_next_lattice_id{0x40000000u};
 // successive driver calls must not reuse Philox streams: each call takes a fresh block of replica ids
@@ -474,6 +485,7 @@ void MonteCarloRenormalizationGroup::calc_critical_exponent(int n_samples_eq, in
     const int per_replica = (n_samples + R - 1) / R;  // every chain takes ceil(n/R): SURVEY 7.0-9, no negative remainder
     const int n_lv = mcrg_levels_full(N);             // floor(log N / log b) - 1, mcrg.cpp:43
     const int spu = settings().sweeps_per_update;
+    mcrg_b200::warn_if_metropolis_is_short(N, n_samples_eq);
     mcrg_b200::DeviceGroup group(N, R, mcrg_b200::take_batch_base(R));
     group.each([&](DeviceBatch &b) {
         ck(mcrg_set_couplings(b.ctx, &K, 1), "mcrg_set_couplings");
@@ -552,6 +564,7 @@ double MonteCarloRenormalizationGroup::approx_critical_point(int n_samples_eq, i
     mcrg_acc_layout lay;
     ck(mcrg_accumulators_layout(&lay), "mcrg_accumulators_layout");
 
+    mcrg_b200::warn_if_metropolis_is_short(L, n_samples_eq);
     DeviceBatch big(L, R, mcrg_b200::take_batch_base(R)), small(S, R, mcrg_b200::take_batch_base(R));
     for (DeviceBatch *b : {&big, &small}) {
         ck(mcrg_set_couplings(b->ctx, &K, 1), "mcrg_set_couplings");
