@@ -237,9 +237,11 @@ __device__ __forceinline__ uint32_t mc_word_id(const McWalk &k, const McConst &g
 
 // NZ < 0: any thresholds;  NZ = 0..3: thresholds with T4 < 1/4 whose planes 2 and 3 are NZ (see mc_compare4_nz)
 // CHK: the thread may have fewer rows than the loop runs steps (it >= n_act: step predicated off)
+// Updates one word and steps to the next row; eq = its lanes still undecided after pass 1 (0: none), sel = its A == 1 lanes.
 template <int WT, int P, bool B32, int NZ, bool CHK>
-__device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
-    uint32_t eq = 0, sel = 0;
+__device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it, uint32_t &eq, uint32_t &sel) {
+    eq = 0u;
+    sel = 0u;
     if (!CHK || it < g.n_act) {
         const uint32_t t = *k.pc;
         const uint32_t d = k.po[g.W];
@@ -273,28 +275,42 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it) {
         k.u = k.n0;
         k.n0 = d;
     }
-    // ~10 % of the words keep undecided lanes, i.e. almost every warp-row has a few: keep this block short
-    const unsigned pend = __ballot_sync(0xFFFFFFFFu, eq != 0u);
-    if (eq != 0u) {
-        const int slot = k.n_queued + __popc(pend & g.lanes_below);
-        if (slot < g.qcap) {
-            g.my_q[slot] = make_uint4(k.off, eq, sel, 0u);
-        } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
-            *k.pc ^= mc_finish(eq, sel, 2, g.tab, g.head, g.seed, mc_word_id(k, g), g.c3_base);
-        }
-    }
-    k.n_queued += __popc(pend);
     k.pc += g.W;
     k.po += g.W;
     k.off += (uint32_t)g.W;
     k.yw += (uint32_t)g.W;
 }
 
+// Append the words of this step that keep undecided lanes to the warp's queue; `back` = rows between the word and the walker's
+// current position (the walker has already stepped past it).  Every lane of the warp calls this.
+__device__ __forceinline__ void mc_push(McWalk &k, const McConst &g, unsigned pend, bool need, int back, uint32_t eq, uint32_t sel) {
+    if (need) {
+        const int slot = k.n_queued + __popc(pend & g.lanes_below);
+        const uint32_t off = k.off - (uint32_t)(back * g.W);
+        if (slot < g.qcap) {
+            g.my_q[slot] = make_uint4(off, eq, sel, 0u);
+        } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
+            const uint32_t yw = k.yw - (uint32_t)(back * g.W);
+            k.pc[-back * g.W] ^= mc_finish(eq, sel, 2, g.tab, g.head, g.seed, (yw & g.yw_mask) | g.wid_c, g.c3_base);
+        }
+    }
+    k.n_queued += __popc(pend);
+}
+
+// Two rows per step.  ~10 % of the words keep undecided lanes, i.e. almost every warp-row has a few, so the queue push is on the
+// critical path of every row: the two rows of a step share ONE push — a lane with one pending word (20 % of the lanes) appends
+// it, and only when some lane of the warp has both words pending (a third of the steps) a second push takes those.
 template <int WT, int P0, bool B32, int NZ, bool CHK>
 __device__ __forceinline__ void mc_walk(McWalk &k, const McConst &g, int n_steps) {
     for (int it = 0; it < n_steps; it += 2) {  // n_steps is even
-        mc_row<WT, P0, B32, NZ, CHK>(k, g, it);
-        mc_row<WT, 1 - P0, B32, NZ, CHK>(k, g, it + 1);
+        uint32_t eq_a, sel_a, eq_b, sel_b;
+        mc_row<WT, P0, B32, NZ, CHK>(k, g, it, eq_a, sel_a);
+        mc_row<WT, 1 - P0, B32, NZ, CHK>(k, g, it + 1, eq_b, sel_b);
+        const bool a = eq_a != 0u, b = eq_b != 0u;
+        const unsigned pend = __ballot_sync(0xFFFFFFFFu, a | b);
+        mc_push(k, g, pend, a | b, a ? 2 : 1, a ? eq_a : eq_b, a ? sel_a : sel_b);
+        const unsigned both = __ballot_sync(0xFFFFFFFFu, a & b);
+        if (both != 0u) mc_push(k, g, both, a & b, 1, eq_b, sel_b);  // warp-uniform branch
     }
 }
 
