@@ -80,6 +80,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
+// ---- programmatic dependent launch: a kernel launched with the programmatic-serialization attribute (launch_pdl) may have its
+// CTAs scheduled while the previous kernel of the stream is still draining; it must not touch global memory before pdl_wait(),
+// which returns once every prerequisite grid has completed and its writes are visible.  pdl_trigger() lets the NEXT kernel's
+// CTAs be scheduled as soon as every CTA of this grid has passed it.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
 }
@@ -593,11 +600,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     s.L = L;
     s.y_first = (y0 - a.H) & (L - 1);
     const uint32_t *src_r = a.src + (size_t)r * 2 * L * W;
+    if (a.trig == 0) pdl_trigger();
     // staging: TMA bulk copies signalled through an mbarrier when rows are 16-byte multiples (L >= 256), else plain loads
     const bool tma = tile_stage_begin(&bar, W, 2u * (uint32_t)rows * (uint32_t)W * 4u);
+    if (MEASURE && threadIdx.x < 4) red[threadIdx.x] = 0;
+    pdl_wait();  // nothing above reads or writes global memory
     tile_stage_plane(tma, &bar, s0_plane(s, 0), src_r, s.y_first, rows, W, L);
     tile_stage_plane(tma, &bar, s0_plane(s, 1), src_r + (size_t)L * W, s.y_first, rows, W, L);
-    if (MEASURE && threadIdx.x < 4) red[threadIdx.x] = 0;
     if (a.nsw > 0) {
         for (int k = threadIdx.x; k < 64; k += blockDim.x) {  // blockDim may be as small as 32
             const uint32_t T = (k & 1) ? a.T8[r] : a.T4[r];
@@ -640,6 +649,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
             atomicAdd(&a.cnt[((size_t)r * (MAX_LEVELS + 1) + 0) * 4 + threadIdx.x], (unsigned long long)red[threadIdx.x]);
     }
 
+    if (a.trig == 1) pdl_trigger();
     if (a.nsw > 0) {
         McQueue q;
         q.ent = reinterpret_cast<uint4 *>(smem + ((2 * rows * W + 3) & ~3));
@@ -649,6 +659,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
             mc_half_sweep_strip(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, a.seed, replica,
                           t + (unsigned long long)(h >> 1));
         uint32_t *dst_r = a.dst + (size_t)r * 2 * L * W;
+        if (a.trig == 2) pdl_trigger();
         if (tma) {  // the R rows of a strip are contiguous in global memory: one bulk store per colour plane
             fence_proxy_async();  // this thread's shared-memory writes become visible to the copy engine ...
             __syncthreads();      // ... and so do everybody else's
@@ -677,9 +688,11 @@ __global__ void __launch_bounds__(MCRG_LEVEL_THREADS, MCRG_LEVEL_MIN_BLOCKS) k_l
     s.W = Wn;
     s.bits = nat_bits(Ln);
     s.mask = valid_mask(s.bits);
+    pdl_trigger();
     const bool tma = tile_stage_begin(&bar, Wn, (uint32_t)(a.R + 1) * (uint32_t)Wn * 4u);
-    tile_stage_plane(tma, &bar, smem, a.in + (size_t)r * Ln * Wn, y0, a.R + 1, Wn, Ln);
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
+    pdl_wait();
+    tile_stage_plane(tma, &bar, smem, a.in + (size_t)r * Ln * Wn, y0, a.R + 1, Wn, Ln);
     const unsigned long long t = *a.d_t + a.t_off;
     const uint32_t replica = a.replica_base + (uint32_t)r;
     tile_stage_wait(tma, &bar);
@@ -914,8 +927,10 @@ __global__ void __launch_bounds__(256) k_tail(const TailArgs a) {
     __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.x;
     const uint32_t replica = a.replica_base + (uint32_t)r;
-    const unsigned long long t = *a.d_t + a.t_off;
+    pdl_trigger();
     for (int k = threadIdx.x; k < (MAX_LEVELS + 1) * 4; k += blockDim.x) red[k] = 0;
+    pdl_wait();
+    const unsigned long long t = *a.d_t + a.t_off;
     if (a.start <= a.n_levels) {  // uniform for the CTA
         const int Ln = a.L >> a.start, Wn = nat_words(Ln);
         const bool tma = tile_stage_begin(&bar, Wn, (uint32_t)Ln * (uint32_t)Wn * 4u);
@@ -1427,13 +1442,45 @@ void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int fo
     }
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait): when the previous operation of the stream is a
+// kernel, this kernel's CTAs may be scheduled — and run their prologue: shared-memory tables, mbarrier set-up — while that one is
+// still draining.  Only for kernels that call pdl_wait() before their first global access.  MCRG_PDL=0 launches the plain way.
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("MCRG_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+
+template <typename Args>
+void launch_pdl(void (*kernel)(Args), dim3 grid, int threads, size_t smem, cudaStream_t st, const Args &a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st) {
     sweep0_max_smem();
     const size_t smem = sweep0_smem_bytes(a.L, a.R, a.H);
     const dim3 grid(a.strips, n_replicas);
     const int threads = sweep0_threads(a.L, a.R, a.H);
-    if (measure) k_sweep0<true><<<grid, threads, smem, st>>>(a);
-    else k_sweep0<false><<<grid, threads, smem, st>>>(a);
+    SweepArgs b = a;
+    if (b.trig < 0) {
+        // Measured (profiles/r2/pdl_ab.txt): releasing the next kernel at the top of this one lets its CTAs settle on whatever
+        // slots are free while this grid still runs — uneven over the SMs when the grid is less than a wave (one 4096^2 replica:
+        // -8 %); released just before the store, the next grid is scheduled into the slots of a finished wave and only its
+        // launch latency and prologue overlap the drain: +21 % for one 4096^2 replica, +1..3 % for C3 / C4 / C5 sweep-only.
+        static const int forced = [] { const char *e = getenv("MCRG_PDL_TRIG"); return e ? atoi(e) : -1; }();
+        b.trig = forced >= 0 ? forced : 2;
+    }
+    if (measure) launch_pdl(k_sweep0<true>, grid, threads, smem, st, b);
+    else launch_pdl(k_sweep0<false>, grid, threads, smem, st, b);
 }
 
 void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st) {
@@ -1441,9 +1488,9 @@ void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st) {
     const int Wn = nat_words(a.Ln);
     const size_t smem = (size_t)(a.R + 1) * Wn * sizeof(uint32_t);
     const dim3 grid(a.strips, n_replicas);
-    k_level<<<grid, pick_threads((long long)a.R * Wn, MCRG_LEVEL_THREADS), smem, st>>>(a);
+    launch_pdl(k_level, grid, pick_threads((long long)a.R * Wn, MCRG_LEVEL_THREADS), smem, st, a);
 }
 
-void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st) { k_tail<<<n_replicas, 256, 0, st>>>(a); }
+void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st) { launch_pdl(k_tail, dim3(n_replicas), 256, 0, st, a); }
 
 }  // namespace mcrg
