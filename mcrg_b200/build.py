@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcrg_b200.so")
 SOURCES = ["capi.cu", "kernels.cu", "cluster.cu", "rgnn.cu", "util_kernels.cu", "comm.cu", "hostpack.cpp"]
 HEADERS = ["bitops.cuh", "tile.cuh", "mcfast.cuh", "kernels.cuh", "capi_internal.cuh"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-t", "0", "-Xcompiler", "-fPIC",
               "-shared", "-ldl"]
 
 

@@ -50,7 +50,10 @@ struct GraphKey {
 
 // Samples in flight: sample s measures into slot s % PYR_SLOTS (its own set of blocked lattices and popcount cells) and its
 // pyramid runs on that slot's side stream, so up to PYR_SLOTS pyramids overlap each other and the sweeps that follow.
-constexpr int PYR_SLOTS = 4;
+#ifndef MCRG_PYR_SLOTS
+#define MCRG_PYR_SLOTS 4
+#endif
+constexpr int PYR_SLOTS = MCRG_PYR_SLOTS;
 
 struct mcrg_ctx {
     int device = 0, L = 0, W = 0, bits = 0, n_replicas = 0, n_bins = 1, full_levels = 0;
@@ -63,6 +66,7 @@ struct mcrg_ctx {
     cudaEvent_t ev_meas[PYR_SLOTS] = {}, ev_pyr[PYR_SLOTS] = {};
     bool pyr_pending[PYR_SLOTS] = {};
     int overlap = 1;      // run the pyramids on the side streams
+    int pdl = 1;          // programmatic dependent launch of k_sweep0 / k_level / k_tail (MCRG_PDL)
     int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
     int resident_threads = 0;    // 0: one thread per column walker (kernels.cu: resident_threads); MCRG_RESIDENT_THREADS forces a block size
@@ -258,7 +262,7 @@ void enqueue_sweeps(mcrg_ctx *c, int n, unsigned long long t_off) {
         const int k = (n - done) < fuse ? (n - done) : fuse;
         const int R = choose_R(c, 2 * k);
         SweepArgs a = sweep_args(c, R, k, t_off + done);
-        launch_sweep0(a, c->n_replicas, false, c->stream);
+        launch_sweep0(a, c->n_replicas, false, c->stream, c->pdl);
         c->cur ^= 1;
         done += k;
     }
@@ -319,7 +323,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     const int R = choose_R(c, 2);
     SweepArgs a = sweep_args(c, R, first, t_off, parity);
     if (probe) cudaEventRecord(probe[0], c->stream);
-    launch_sweep0(a, c->n_replicas, true, c->stream);
+    launch_sweep0(a, c->n_replicas, true, c->stream, c->pdl);
     if (probe) cudaEventRecord(probe[1], c->stream);
     if (first) c->cur ^= 1;
     if (overlap) {
@@ -343,7 +347,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
         la.level = lv;
         la.R = choose_Rn(la.Ln);
         la.strips = la.Ln / la.R;
-        launch_level(la, c->n_replicas, s_pyr);
+        launch_level(la, c->n_replicas, s_pyr, c->pdl);
         ++lv;
     }
     TailArgs ta;
@@ -367,7 +371,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     ta.bin = bin;
     ta.accumulate = accumulate;
     if (probe) cudaEventRecord(probe[2], c->stream);
-    launch_tail(ta, c->n_replicas, s_pyr);
+    launch_tail(ta, c->n_replicas, s_pyr, c->pdl);
     if (probe) cudaEventRecord(probe[3], c->stream);
     if (overlap) {
         cudaEventRecord(c->ev_pyr[parity], s_pyr);
@@ -503,6 +507,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
         CK(cudaEventCreateWithFlags(&c->ev_pyr[p], cudaEventDisableTiming));
     }
     if (const char *e = getenv("MCRG_OVERLAP")) c->overlap = atoi(e);
+    if (const char *e = getenv("MCRG_PDL")) c->pdl = atoi(e) != 0;
     if (const char *e = getenv("MCRG_RESIDENT")) c->resident = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT_THREADS")) c->resident_threads = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT_MAX_SAMPLES")) {

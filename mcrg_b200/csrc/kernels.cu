@@ -1444,14 +1444,10 @@ void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int fo
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait): when the previous operation of the stream is a
 // kernel, this kernel's CTAs may be scheduled — and run their prologue: shared-memory tables, mbarrier set-up — while that one is
-// still draining.  Only for kernels that call pdl_wait() before their first global access.  MCRG_PDL=0 launches the plain way.
-bool pdl_enabled() {
-    static const bool on = [] { const char *e = getenv("MCRG_PDL"); return !(e && atoi(e) == 0); }();
-    return on;
-}
-
+// still draining.  Only for kernels that call pdl_wait() before their first global access.  pdl = false launches the plain way
+// (per context: MCRG_PDL=0).
 template <typename Args>
-void launch_pdl(void (*kernel)(Args), dim3 grid, int threads, size_t smem, cudaStream_t st, const Args &a) {
+void launch_pdl(void (*kernel)(Args), dim3 grid, int threads, size_t smem, cudaStream_t st, bool pdl, const Args &a) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3((unsigned)threads);
@@ -1461,11 +1457,11 @@ void launch_pdl(void (*kernel)(Args), dim3 grid, int threads, size_t smem, cudaS
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st) {
+void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st, bool pdl) {
     sweep0_max_smem();
     const size_t smem = sweep0_smem_bytes(a.L, a.R, a.H);
     const dim3 grid(a.strips, n_replicas);
@@ -1479,18 +1475,18 @@ void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_
         static const int forced = [] { const char *e = getenv("MCRG_PDL_TRIG"); return e ? atoi(e) : -1; }();
         b.trig = forced >= 0 ? forced : 2;
     }
-    if (measure) launch_pdl(k_sweep0<true>, grid, threads, smem, st, b);
-    else launch_pdl(k_sweep0<false>, grid, threads, smem, st, b);
+    if (measure) launch_pdl(k_sweep0<true>, grid, threads, smem, st, pdl, b);
+    else launch_pdl(k_sweep0<false>, grid, threads, smem, st, pdl, b);
 }
 
-void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st) {
+void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st, bool pdl) {
     sweep0_max_smem();
     const int Wn = nat_words(a.Ln);
     const size_t smem = (size_t)(a.R + 1) * Wn * sizeof(uint32_t);
     const dim3 grid(a.strips, n_replicas);
-    launch_pdl(k_level, grid, pick_threads((long long)a.R * Wn, MCRG_LEVEL_THREADS), smem, st, a);
+    launch_pdl(k_level, grid, pick_threads((long long)a.R * Wn, MCRG_LEVEL_THREADS), smem, st, pdl, a);
 }
 
-void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st) { launch_pdl(k_tail, dim3(n_replicas), 256, 0, st, a); }
+void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st, bool pdl) { launch_pdl(k_tail, dim3(n_replicas), 256, 0, st, pdl, a); }
 
 }  // namespace mcrg

@@ -153,9 +153,9 @@ struct SwArgs {
 void launch_sw_update(const SwArgs &a, int n_replicas, cudaStream_t st);
 
 void launch_resident(const ResidentArgs &a, int n_replicas, bool measure, int forced_threads, cudaStream_t st);
-void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st);
-void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st);
-void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st);
+void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_t st, bool pdl);  // pdl: see launch_pdl (kernels.cu)
+void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st, bool pdl);
+void launch_tail(const TailArgs &a, int n_replicas, cudaStream_t st, bool pdl);
 void launch_total_limbs(const unsigned long long *lo, const long long *hi, int n_rb, long long *out, cudaStream_t st);
 void launch_rgnn(const uint32_t *planes, int L, int n_replicas, const double *W, double h, double *u_out, double *grad_out,
                  double *acc, int accumulate, cudaStream_t st);

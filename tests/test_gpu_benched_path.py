@@ -72,18 +72,20 @@ def test_graph_replay_strip_run_matches_oracle(mc, L, Ks, n1, n2, m, max_levels,
 
 
 def test_graph_run_equals_plain_launches_at_full_size(mc):
-    """L = 4096, 40 replicas x 5 couplings (exactly bench.py's context), 48 samples: graphs + side-stream pyramid against the
-    same run with plain launches on one stream — every accumulator and every spin identical (the oracle cannot do this volume;
-    the plain-launch path is the one the oracle-pinned tests above and in test_gpu_parity.py cover at L <= 4096)."""
+    """L = 4096, 40 replicas x 5 couplings (exactly bench.py's context), 48 samples: graphs + side-stream pyramid + programmatic
+    dependent launch against the same run with plain launches on one stream, and against graphs without programmatic launch —
+    every accumulator and every spin identical (the oracle cannot do this volume; the plain-launch path is the one the
+    oracle-pinned tests above and in test_gpu_parity.py cover at L <= 4096)."""
     import bench
 
     L, R, n = 4096, 40, 48
     Ks = np.repeat(bench.TRAIN_KS, 8)
     out = []
-    for graphs, overlap in ((1, "1"), (0, "0")):
+    for graphs, overlap, pdl in ((1, "1", "1"), (0, "0", "0"), (1, "1", "0")):
         import os
 
         os.environ["MCRG_OVERLAP"] = overlap
+        os.environ["MCRG_PDL"] = pdl
         try:
             with mc.Context(L, R, seed=12345) as ctx:
                 ctx.set_tuning(use_graphs=graphs)
@@ -97,10 +99,12 @@ def test_graph_run_equals_plain_launches_at_full_size(mc):
                 out.append((acc, accd, obs, ctx.get_spins(0, 2)))
         finally:
             del os.environ["MCRG_OVERLAP"]
-    a, b = out
-    assert (a[0] == b[0]).all() and np.array_equal(a[1], b[1])
-    for k in ("Snn", "Snnn", "Splaq", "M"):
-        assert np.array_equal(a[2][k], b[2][k])
-    assert np.array_equal(a[3], b[3])
+            del os.environ["MCRG_PDL"]
+    a = out[0]
+    for b in out[1:]:
+        assert (a[0] == b[0]).all() and np.array_equal(a[1], b[1])
+        for k in ("Snn", "Snnn", "Splaq", "M"):
+            assert np.array_equal(a[2][k], b[2][k])
+        assert np.array_equal(a[3], b[3])
     lay = mc.capi.acc_layout()
     assert all(a[0][r, 0, lay.slot_n] == 2 * n for r in range(R))
