@@ -48,30 +48,36 @@ struct GraphKey {
 
 }  // namespace
 
-// Samples in flight: sample s measures into slot s % PYR_SLOTS (its own set of blocked lattices and popcount cells) and its
-// pyramid runs on that slot's side stream, so up to PYR_SLOTS pyramids overlap each other and the sweeps that follow.
+// Samples in flight: sample s measures into slot s % n_slots (its own set of blocked lattices and popcount cells) and its
+// pyramid runs on that slot's side stream, so up to n_slots pyramids overlap each other and the sweeps that follow.  The slot
+// count is chosen per context (choose_slots): as many as the largest graph holds samples when the blocked lattices are small
+// enough, so that inside a graph no measuring sweep ever waits for a pyramid to free its slot.
 #ifndef MCRG_PYR_SLOTS
-#define MCRG_PYR_SLOTS 4
+#define MCRG_PYR_SLOTS 64
 #endif
-constexpr int PYR_SLOTS = MCRG_PYR_SLOTS;
+constexpr int PYR_SLOTS = MCRG_PYR_SLOTS;  // upper bound (array sizes)
+// Samples per CUDA graph of mcrg_run: the large one while that many samples remain, then the small one, then plain launches.
+// Every graph ends with a join (the side streams come back, the sweep counter advances): fewer, longer graphs lose less there.
+constexpr int GRAPH_CHUNK_LARGE = 64, GRAPH_CHUNK_SMALL = 16;
 
 struct mcrg_ctx {
     int device = 0, L = 0, W = 0, bits = 0, n_replicas = 0, n_bins = 1, full_levels = 0;
     uint64_t seed = 0;
     uint32_t replica_base = 0;
     cudaStream_t stream = nullptr;   // sweeps (and everything else)
-    cudaStream_t stream2[PYR_SLOTS] = {};  // blocked-level pyramid of sample s (stream2[s % PYR_SLOTS]), overlapped with the sweeps of
+    cudaStream_t stream2[PYR_SLOTS] = {};  // blocked-level pyramid of sample s (stream2[s % c->n_slots]), overlapped with the sweeps of
                                            // the next samples and with the pyramids of its neighbours (their accumulation excepted)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_meas[PYR_SLOTS] = {}, ev_pyr[PYR_SLOTS] = {};
     bool pyr_pending[PYR_SLOTS] = {};
+    int n_slots = 4;      // slots in use (<= PYR_SLOTS)
     int overlap = 1;      // run the pyramids on the side streams
     int pdl = 1;          // programmatic dependent launch of k_sweep0 / k_level / k_tail (MCRG_PDL)
     int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
     int resident_threads = 0;    // 0: one thread per column walker (kernels.cu: resident_threads); MCRG_RESIDENT_THREADS forces a block size
     int last_parity = 0;  // which slot (blocked lattices / popcount cells) the last measurement used
-    size_t levels_words = 0, cnt_cells = 0;  // words of one set of blocked lattices (PYR_SLOTS sets)
+    size_t levels_words = 0, cnt_cells = 0;  // words of one set of blocked lattices (n_slots sets)
     uint32_t *planes[2] = {nullptr, nullptr};
     int cur = 0;
     uint32_t *levels = nullptr;
@@ -494,15 +500,46 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     *out = c;  // so that a failure below can still be cleaned up by mcrg_ctx_destroy
     sweep0_max_smem();  // opt in to large dynamic shared memory once, outside any stream capture
     CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+    size_t off = 0;
+    for (int lv = 1; lv <= (c->full_levels > 1 ? c->full_levels : 1); ++lv) {  // level 1 always exists: k_sweep0 writes it
+        const int Ln = L >> lv;
+        c->level_off[lv] = off;
+        size_t words = ((size_t)n_replicas * Ln * nat_words(Ln) + 3) & ~(size_t)3;  // 16-byte aligned for 128-bit loads
+        off += words;
+    }
+    c->levels_words = off + 4;  // one set of blocked lattices; n_slots sets are allocated (see enqueue_sample)
+    const size_t n_cnt = (size_t)n_replicas * (MAX_LEVELS + 1) * 4;
+    c->cnt_cells = n_cnt;
     {
+        // Slots (samples in flight): one per sample of the largest graph when that costs at most 4 GiB (C4: 64 x 28 MB), halved
+        // until it does; lattices that run on the resident kernel never use more than one (their pyramids stay in shared memory),
+        // so they get the minimum.  MCRG_SLOTS overrides (experiments, tests).  Results never depend on the count.
+        const size_t per_slot = c->levels_words * 4 + n_cnt * 8;
+        int n = L <= RESIDENT_MAX_L ? 4 : (PYR_SLOTS < GRAPH_CHUNK_LARGE ? PYR_SLOTS : GRAPH_CHUNK_LARGE);
+        while (n > 4 && (size_t)n * per_slot > ((size_t)4 << 30)) n >>= 1;
+        if (const char *e = getenv("MCRG_SLOTS")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= PYR_SLOTS) n = v;
+        }
+        c->n_slots = n;
+    }
+    {
+        // The sweeps are the critical path of a run (sample s+1 cannot start before the sweep of sample s is done, a pyramid only
+        // has to finish before its slot comes round again): the sweep stream gets the high priority, the pyramid streams the low
+        // one, and the graphs are instantiated with per-node priorities (mcrg_run) — otherwise every node of a graph runs at the
+        // priority of the stream the graph is launched into.  Measured (profiles/r2/priority_slots_ab.txt): pyramids above the
+        // sweeps C4 m=1 -4 %, below +0.8 % (C5 +2 %).  MCRG_PYR_PRIO = hi | same | lo (default) for experiments.
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
-        for (int p = 0; p < PYR_SLOTS; ++p) CK(cudaStreamCreateWithPriority(&c->stream2[p], cudaStreamNonBlocking, prio_hi));  // small kernels first
+        const char *pp = getenv("MCRG_PYR_PRIO");
+        const bool pyr_hi = pp && !strcmp(pp, "hi"), pyr_same = pp && !strcmp(pp, "same");
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, (pyr_hi || pyr_same) ? prio_lo : prio_hi));
+        for (int p = 0; p < c->n_slots; ++p)
+            CK(cudaStreamCreateWithPriority(&c->stream2[p], cudaStreamNonBlocking, pyr_hi ? prio_hi : prio_lo));
     }
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    for (int p = 0; p < PYR_SLOTS; ++p) {
+    for (int p = 0; p < c->n_slots; ++p) {
         CK(cudaEventCreateWithFlags(&c->ev_meas[p], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_pyr[p], cudaEventDisableTiming));
     }
@@ -517,22 +554,12 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
     const size_t plane_words = (size_t)n_replicas * 2 * L * c->W;
     CK(cudaMalloc(&c->planes[0], plane_words * 4));
     CK(cudaMalloc(&c->planes[1], plane_words * 4));
-    size_t off = 0;
-    for (int lv = 1; lv <= (c->full_levels > 1 ? c->full_levels : 1); ++lv) {  // level 1 always exists: k_sweep0 writes it
-        const int Ln = L >> lv;
-        c->level_off[lv] = off;
-        size_t words = ((size_t)n_replicas * Ln * nat_words(Ln) + 3) & ~(size_t)3;  // 16-byte aligned for 128-bit loads
-        off += words;
-    }
-    c->levels_words = off + 4;  // PYR_SLOTS sets of blocked lattices (see enqueue_sample)
-    CK(cudaMalloc(&c->levels, PYR_SLOTS * c->levels_words * 4));
-    CK(cudaMemsetAsync(c->levels, 0, PYR_SLOTS * c->levels_words * 4, c->stream));
+    CK(cudaMalloc(&c->levels, (size_t)c->n_slots * c->levels_words * 4));
+    CK(cudaMemsetAsync(c->levels, 0, (size_t)c->n_slots * c->levels_words * 4, c->stream));
     CK(cudaMalloc(&c->d_level_off, sizeof(c->level_off)));
     CK(cudaMemcpyAsync(c->d_level_off, c->level_off, sizeof(c->level_off), cudaMemcpyHostToDevice, c->stream));
-    const size_t n_cnt = (size_t)n_replicas * (MAX_LEVELS + 1) * 4;
-    c->cnt_cells = n_cnt;
-    CK(cudaMalloc(&c->cnt, PYR_SLOTS * n_cnt * 8));
-    CK(cudaMemsetAsync(c->cnt, 0, PYR_SLOTS * n_cnt * 8, c->stream));
+    CK(cudaMalloc(&c->cnt, (size_t)c->n_slots * n_cnt * 8));
+    CK(cudaMemsetAsync(c->cnt, 0, (size_t)c->n_slots * n_cnt * 8, c->stream));
     CK(cudaMalloc(&c->S_out, n_cnt * 8));
     CK(cudaMemsetAsync(c->S_out, 0, n_cnt * 8, c->stream));
     const size_t n_acc = (size_t)n_replicas * n_bins * N_SLOTS;
@@ -973,49 +1000,54 @@ int mcrg_run(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int max_levels, 
     choose_R(c, 2);  // strip heights are chosen (occupancy queries) before any stream capture starts
     for (int k = 1; k <= c->fuse_sweeps; ++k) choose_R(c, 2 * k);
     if (c->use_graphs) {
-        const int chunk = 16;
-        while (n_samples - done >= chunk) {
-            GraphKey key{m, n_lv, bin, chunk, c->cur, c->strip_rows, c->fuse_sweeps, c->update_mode};
-            auto it = c->graphs.find(key);
-            const int cur_before = c->cur;
-            if (it == c->graphs.end()) {
-                cudaGraph_t g = nullptr;
-                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s % PYR_SLOTS);
-                join_pyramids(c);  // every graph is self-contained: the side streams join back before the capture ends
-                launch_advance_t(c->d_t, (unsigned long long)chunk * m, c->stream);
-                cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-                if (e != cudaSuccess) {
-                    c->cur = cur_before;
-                    return fail(MCRG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        static const int forced_chunk = [] { const char *e = getenv("MCRG_GRAPH_CHUNK"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 256) ? v : 0; }();
+        const int tiers[2] = {forced_chunk ? forced_chunk : GRAPH_CHUNK_LARGE, forced_chunk ? forced_chunk : GRAPH_CHUNK_SMALL};
+        for (int tier = 0; tier < 2; ++tier) {
+            const int chunk = tiers[tier];
+            while (n_samples - done >= chunk) {
+                GraphKey key{m, n_lv, bin, chunk, c->cur, c->strip_rows, c->fuse_sweeps, c->update_mode};
+                auto it = c->graphs.find(key);
+                const int cur_before = c->cur;
+                if (it == c->graphs.end()) {
+                    cudaGraph_t g = nullptr;
+                    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                    for (int s = 0; s < chunk; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s % c->n_slots);
+                    join_pyramids(c);  // every graph is self-contained: the side streams join back before the capture ends
+                    launch_advance_t(c->d_t, (unsigned long long)chunk * m, c->stream);
+                    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+                    if (e != cudaSuccess) {
+                        c->cur = cur_before;
+                        return fail(MCRG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+                    }
+                    cudaGraphExec_t ge = nullptr;
+                    static const bool node_prio = [] { const char *e = getenv("MCRG_GRAPH_PRIO"); return !(e && atoi(e) == 0); }();  // see mcrg_ctx_create
+                    e = cudaGraphInstantiate(&ge, g, node_prio ? cudaGraphInstantiateFlagUseNodePriority : 0);
+                    cudaGraphDestroy(g);
+                    if (e != cudaSuccess) {
+                        c->cur = cur_before;
+                        return fail(MCRG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+                    }
+                    it = c->graphs.emplace(key, ge).first;
+                    // the capture advanced c->cur exactly as a replay will
+                } else {
+                    // replay flips the ping-pong index as often as the capture did
+                    int flips_per_sample = m > 0 ? 1 : 0;
+                    if (m > 1) flips_per_sample += (m - 1 + c->fuse_sweeps - 1) / c->fuse_sweeps;
+                    if (c->update_mode == MCRG_UPDATE_CLUSTER) flips_per_sample = 0;  // cluster updates work in place
+                    if ((chunk * flips_per_sample) & 1) c->cur ^= 1;
+                    c->last_levels = n_lv;
+                    c->last_parity = (chunk - 1) % c->n_slots;
+                    c->measured = true;
                 }
-                cudaGraphExec_t ge = nullptr;
-                e = cudaGraphInstantiate(&ge, g, 0);
-                cudaGraphDestroy(g);
-                if (e != cudaSuccess) {
-                    c->cur = cur_before;
-                    return fail(MCRG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-                }
-                it = c->graphs.emplace(key, ge).first;
-                // the capture advanced c->cur exactly as a replay will
-            } else {
-                // replay flips the ping-pong index as often as the capture did
-                int flips_per_sample = m > 0 ? 1 : 0;
-                if (m > 1) flips_per_sample += (m - 1 + c->fuse_sweeps - 1) / c->fuse_sweeps;
-                if (c->update_mode == MCRG_UPDATE_CLUSTER) flips_per_sample = 0;  // cluster updates work in place
-                if ((chunk * flips_per_sample) & 1) c->cur ^= 1;
-                c->last_levels = n_lv;
-                c->last_parity = (chunk - 1) % PYR_SLOTS;
-                c->measured = true;
+                CK(cudaGraphLaunch(it->second, c->stream));
+                c->t_host += (unsigned long long)chunk * m;
+                done += chunk;
             }
-            CK(cudaGraphLaunch(it->second, c->stream));
-            c->t_host += (unsigned long long)chunk * m;
-            done += chunk;
         }
     }
     const int rest = n_samples - done;
     if (rest > 0) {
-        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s % PYR_SLOTS);
+        for (int s = 0; s < rest; ++s) enqueue_sample(c, n_lv, m, 1, bin, (unsigned long long)s * m, s % c->n_slots);
         join_pyramids(c);
         if (m > 0) launch_advance_t(c->d_t, (unsigned long long)rest * m, c->stream);
         c->t_host += (unsigned long long)rest * m;
@@ -1032,7 +1064,7 @@ int mcrg_profile_kernels(mcrg_ctx *c, int n_samples, int sweeps_per_sample, int 
     const int m = sweeps_per_sample;
     std::vector<cudaEvent_t> ev((size_t)n_samples * 5);
     for (auto &e : ev) CK(cudaEventCreate(&e));
-    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, s % PYR_SLOTS, &ev[(size_t)s * 5]);
+    for (int s = 0; s < n_samples; ++s) enqueue_sample(c, n_lv, m, 1, 0, (unsigned long long)s * m, s % c->n_slots, &ev[(size_t)s * 5]);
     if (m > 0) launch_advance_t(c->d_t, (unsigned long long)n_samples * m, c->stream);
     c->t_host += (unsigned long long)n_samples * m;
     CK(cudaGetLastError());

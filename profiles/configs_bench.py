@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--samples", type=int, default=0, help="samples / sweeps per timed call (default 64 for L <= 1024, else 32)")
     a = ap.parse_args()
     rows = []
     for name, L, R, lv in CONFIGS:
@@ -31,7 +32,7 @@ def main():
             ctx.set_couplings([KC])
             ctx.init_hot()
             ctx.sweep(20)
-            n = 64 if L <= 1024 else 32
+            n = a.samples if a.samples > 0 else (64 if L <= 1024 else 32)
             res = {}
             for mode, fn in (("sweep_only", lambda: ctx.sweep(n)), ("m=1", lambda: ctx.run(n, 1, lv, 0)), ("m=16", lambda: ctx.run(max(n // 8, 2), 16, lv, 0))):
                 fn()

@@ -33,6 +33,7 @@ CASES = [
     (4096, [KC, -0.4320459], 17, 0, 1, -1, 0),         # the headline shape: one graph + 1 sample
     (512, [KC, -0.42], 34, 18, 1, -1, 32),             # forced strips below the resident limit (one k_tail-only pyramid)
     (1024, [KC, -0.45], 18, 16, 1, -1, 44),            # strips that do not divide L, unaligned to the tie-coin chunks
+    (1024, [KC, -0.4320459], 81, 64, 1, -1, 0),        # 64-sample graph + 16-sample graph + 1; then the cached 64-sample graph
 ]
 
 
@@ -69,6 +70,32 @@ def test_graph_replay_strip_run_matches_oracle(mc, L, Ks, n1, n2, m, max_levels,
                 assert np.array_equal(spins2[r], want2["final"]), (L, r)
                 # a measurement after the replays reads the right ping-pong buffers
                 assert np.array_equal(S_last[r], _libs.pyramid(L, want2["final"], seed, base + r, t0 + (n1 + n2) * m, max_levels)), (L, r)
+
+
+@pytest.mark.parametrize("slots", ["1", "3", "16"])
+def test_results_do_not_depend_on_the_number_of_pyramid_slots(mc, monkeypatch, slots):
+    """Samples in flight (sets of blocked lattices / popcount cells, one side stream each): with fewer slots than a graph has
+    samples a measuring sweep waits for the pyramid that frees its slot; the default (64 at this size) never does inside a graph.
+    Same accumulators, same configurations, same last measurement — the default is pinned to the oracle above."""
+    L, R, n = 1024, 3, 85
+    out = []
+    for env in (None, slots):
+        if env is None:
+            monkeypatch.delenv("MCRG_SLOTS", raising=False)
+        else:
+            monkeypatch.setenv("MCRG_SLOTS", env)
+        with mc.Context(L, R, seed=31, n_bins=1) as ctx:
+            ctx.set_tuning(use_graphs=1)
+            ctx.set_couplings([KC, -0.43, -0.46])
+            ctx.init_hot()
+            ctx.run(n, 1, -1, 0)
+            ctx.run(17, 2, -1, 0)
+            acc, accd = ctx.accumulators()
+            out.append((acc, accd, ctx.measure(-1), ctx.get_spins()))
+    monkeypatch.delenv("MCRG_SLOTS", raising=False)
+    a, b = out
+    assert (a[0] == b[0]).all() and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
 
 
 def test_graph_run_equals_plain_launches_at_full_size(mc):
