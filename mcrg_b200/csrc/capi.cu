@@ -72,7 +72,8 @@ struct mcrg_ctx {
     bool pyr_pending[PYR_SLOTS] = {};
     int n_slots = 4;      // slots in use (<= PYR_SLOTS)
     int overlap = 1;      // run the pyramids on the side streams
-    int pdl = 1;          // programmatic dependent launch of k_sweep0 / k_level / k_tail (MCRG_PDL)
+    int pdl = 3;          // programmatic dependent launch (MCRG_PDL), bits: 1 k_sweep0<false>, 2 k_sweep0<MEASURE>, 4 k_level / k_tail
+                          // (4 measured harmful at m = 1: their early CTAs take slots from the sweeps, profiles/r2/pdl_ab.txt)
     int resident_cap = 1 << 22;  // samples per resident launch (64-bit in-launch sums stay exact); MCRG_RESIDENT_MAX_SAMPLES lowers it
     int resident = 1;     // lattices up to RESIDENT_MAX_L: whole replica in one CTA's shared memory, one launch per call
     int resident_threads = 0;    // 0: one thread per column walker (kernels.cu: resident_threads); MCRG_RESIDENT_THREADS forces a block size
@@ -268,7 +269,7 @@ void enqueue_sweeps(mcrg_ctx *c, int n, unsigned long long t_off) {
         const int k = (n - done) < fuse ? (n - done) : fuse;
         const int R = choose_R(c, 2 * k);
         SweepArgs a = sweep_args(c, R, k, t_off + done);
-        launch_sweep0(a, c->n_replicas, false, c->stream, c->pdl);
+        launch_sweep0(a, c->n_replicas, false, c->stream, (c->pdl & 1) != 0);
         c->cur ^= 1;
         done += k;
     }
@@ -329,7 +330,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     const int R = choose_R(c, 2);
     SweepArgs a = sweep_args(c, R, first, t_off, parity);
     if (probe) cudaEventRecord(probe[0], c->stream);
-    launch_sweep0(a, c->n_replicas, true, c->stream, c->pdl);
+    launch_sweep0(a, c->n_replicas, true, c->stream, (c->pdl & 2) != 0);
     if (probe) cudaEventRecord(probe[1], c->stream);
     if (first) c->cur ^= 1;
     if (overlap) {
@@ -353,7 +354,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
         la.level = lv;
         la.R = choose_Rn(la.Ln);
         la.strips = la.Ln / la.R;
-        launch_level(la, c->n_replicas, s_pyr, c->pdl);
+        launch_level(la, c->n_replicas, s_pyr, (c->pdl & 4) != 0);
         ++lv;
     }
     TailArgs ta;
@@ -377,7 +378,7 @@ void enqueue_sample(mcrg_ctx *c, int n_lv, int m, int accumulate, int bin, unsig
     ta.bin = bin;
     ta.accumulate = accumulate;
     if (probe) cudaEventRecord(probe[2], c->stream);
-    launch_tail(ta, c->n_replicas, s_pyr, c->pdl);
+    launch_tail(ta, c->n_replicas, s_pyr, (c->pdl & 4) != 0);
     if (probe) cudaEventRecord(probe[3], c->stream);
     if (overlap) {
         cudaEventRecord(c->ev_pyr[parity], s_pyr);
@@ -544,7 +545,7 @@ int mcrg_ctx_create(int device, int L, int n_replicas, uint64_t seed, uint32_t r
         CK(cudaEventCreateWithFlags(&c->ev_pyr[p], cudaEventDisableTiming));
     }
     if (const char *e = getenv("MCRG_OVERLAP")) c->overlap = atoi(e);
-    if (const char *e = getenv("MCRG_PDL")) c->pdl = atoi(e) != 0;
+    if (const char *e = getenv("MCRG_PDL")) c->pdl = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT")) c->resident = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT_THREADS")) c->resident_threads = atoi(e);
     if (const char *e = getenv("MCRG_RESIDENT_MAX_SAMPLES")) {

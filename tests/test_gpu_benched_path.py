@@ -108,7 +108,7 @@ def test_graph_run_equals_plain_launches_at_full_size(mc):
     L, R, n = 4096, 40, 48
     Ks = np.repeat(bench.TRAIN_KS, 8)
     out = []
-    for graphs, overlap, pdl in ((1, "1", "1"), (0, "0", "0"), (1, "1", "0")):
+    for graphs, overlap, pdl in ((1, "1", "3"), (0, "0", "0"), (1, "1", "0"), (1, "1", "7")):  # MCRG_PDL bits: sweep, measuring sweep, pyramid
         import os
 
         os.environ["MCRG_OVERLAP"] = overlap
