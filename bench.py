@@ -285,12 +285,13 @@ def run_ours(args, rank, world, local_rank):
     resident = L <= 512 and not args.strip_rows
     n_level_kernels = sum(1 for lv in range(1, n_lv + 1) if (L >> lv) > (512 if n_loc >= 16 else 256))  # capi.cu: tail_start_size
     # strips: per sample k_sweep0<measure>, k_level per large level, k_tail, further sweep launches; per step the sweep-counter
-    # update(s) (one per 16-sample graph + one for the rest) and the limb-total kernel.  resident: one launch per block.
+    # update(s) (one per graph + one for the rest) and the limb-total kernel.  resident: one launch per block.
     extra_sweeps = 0 if m <= 1 else -(-(m - 1) // max(1, args.fuse_sweeps))
     if resident:
         launches_per_step = 1 + 1 + 1
     else:
-        launches_per_step = S * (2 + n_level_kernels + extra_sweeps) + ((S // 16 + (1 if S % 16 else 0)) if args.graphs else 1) + 1
+        n_graphs = S // 64 + (S % 64) // 16 + (1 if S % 16 else 0)  # capi.cu mcrg_run: 64-sample graphs, 16-sample graphs, the rest
+        launches_per_step = S * (2 + n_level_kernels + extra_sweeps) + (n_graphs if args.graphs else 1) + 1
 
     def block():
         ctx.run(S, m, max_lv, 0)
