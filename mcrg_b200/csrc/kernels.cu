@@ -600,7 +600,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
     s.L = L;
     s.y_first = (y0 - a.H) & (L - 1);
     const uint32_t *src_r = a.src + (size_t)r * 2 * L * W;
-    if (a.trig == 0) pdl_trigger();
     // staging: TMA bulk copies signalled through an mbarrier when rows are 16-byte multiples (L >= 256), else plain loads
     const bool tma = tile_stage_begin(&bar, W, 2u * (uint32_t)rows * (uint32_t)W * 4u);
     if (MEASURE && threadIdx.x < 4) red[threadIdx.x] = 0;
@@ -649,7 +648,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
             atomicAdd(&a.cnt[((size_t)r * (MAX_LEVELS + 1) + 0) * 4 + threadIdx.x], (unsigned long long)red[threadIdx.x]);
     }
 
-    if (a.trig == 1) pdl_trigger();
     if (a.nsw > 0) {
         McQueue q;
         q.ent = reinterpret_cast<uint4 *>(smem + ((2 * rows * W + 3) & ~3));
@@ -659,7 +657,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0
             mc_half_sweep_strip(s, h & 1, 1 + h, rows - 2 - 2 * h, lw, anti, &tab, q, a.seed, replica,
                           t + (unsigned long long)(h >> 1));
         uint32_t *dst_r = a.dst + (size_t)r * 2 * L * W;
-        if (a.trig == 2) pdl_trigger();
+        pdl_trigger();  // the next kernel of the stream may be scheduled from here on (see launch_sweep0)
         if (tma) {  // the R rows of a strip are contiguous in global memory: one bulk store per colour plane
             fence_proxy_async();  // this thread's shared-memory writes become visible to the copy engine ...
             __syncthreads();      // ... and so do everybody else's
@@ -1466,17 +1464,12 @@ void launch_sweep0(const SweepArgs &a, int n_replicas, bool measure, cudaStream_
     const size_t smem = sweep0_smem_bytes(a.L, a.R, a.H);
     const dim3 grid(a.strips, n_replicas);
     const int threads = sweep0_threads(a.L, a.R, a.H);
-    SweepArgs b = a;
-    if (b.trig < 0) {
-        // Measured (profiles/r2/pdl_ab.txt): releasing the next kernel at the top of this one lets its CTAs settle on whatever
-        // slots are free while this grid still runs — uneven over the SMs when the grid is less than a wave (one 4096^2 replica:
-        // -8 %); released just before the store, the next grid is scheduled into the slots of a finished wave and only its
-        // launch latency and prologue overlap the drain: +21 % for one 4096^2 replica, +1..3 % for C3 / C4 / C5 sweep-only.
-        static const int forced = [] { const char *e = getenv("MCRG_PDL_TRIG"); return e ? atoi(e) : -1; }();
-        b.trig = forced >= 0 ? forced : 2;
-    }
-    if (measure) launch_pdl(k_sweep0<true>, grid, threads, smem, st, pdl, b);
-    else launch_pdl(k_sweep0<false>, grid, threads, smem, st, pdl, b);
+    // Where k_sweep0 releases the next kernel (pdl_trigger), measured (profiles/r2/pdl_ab.txt): at the top of the kernel the next
+    // grid's CTAs settle on whatever slots are free while this grid still runs — uneven over the SMs when the grid is less than a
+    // wave (one 4096^2 replica: -8 %); just before the store, the next grid is scheduled into the slots of a finished wave and only
+    // its launch latency and prologue overlap the drain: +21 % for one 4096^2 replica, +1..3 % for C3 / C4 / C5 sweep-only.
+    if (measure) launch_pdl(k_sweep0<true>, grid, threads, smem, st, pdl, a);
+    else launch_pdl(k_sweep0<false>, grid, threads, smem, st, pdl, a);
 }
 
 void launch_level(const LevelArgs &a, int n_replicas, cudaStream_t st, bool pdl) {

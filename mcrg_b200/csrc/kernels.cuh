@@ -53,8 +53,6 @@ struct SweepArgs {
     int L, W, bits;
     int R, H, nsw;
     int strips;                // ceil(L / R): the last strip may be shorter
-    int trig = -1;             // where the kernel lets the next kernel's CTAs be scheduled (pdl_trigger): 0 top, 1 before the
-                               // half-sweeps, 2 before the store, 3 at exit; -1: launch_sweep0 decides
 };
 
 struct LevelArgs {
