@@ -336,7 +336,7 @@ __device__ __forceinline__ void mc_walk_b32(bool nz, int xy, int par0, McWalk &k
     else mc_walk_par<WT, true, 3, CHK>(par0, k, g, n_steps);
 }
 
-template <int WT>
+template <int WT, bool REQUEUE = false>
 __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
                                                 const McTable *tab, const McQueue &q, uint64_t seed, uint32_t replica,
                                                 unsigned long long sweep) {
@@ -412,12 +412,57 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
         mc_walk_par<0, false, -1, true>(par0, k, g, n_steps);
     }
     __syncwarp();
-    const int total = min(k.n_queued, q.cap);
-    for (int e = lane; e < total; e += 32) {
-        const uint4 ent = g.my_q[e];
-        const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
-        const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
-        plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, g.head, seed, word_id, g.c3_base);
+    if (!REQUEUE) {  // resident kernels: a warp rarely queues more than one batch per half-sweep; the plain form is faster there
+        const int total = min(k.n_queued, q.cap);
+        for (int e = lane; e < total; e += 32) {
+            const uint4 ent = g.my_q[e];
+            const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
+            const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
+            plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, g.head, seed, word_id, g.c3_base);
+        }
+    } else {
+        // Pass 2, one queue entry per lane.  A batch of 32 entries would run as many Philox calls as its unluckiest entry (after
+        // call 2 a lane is still undecided with probability 1/16: 90 % of the full batches need a second round for one or two lanes).
+        // So every batch but the last runs exactly ONE call and appends the entries that still have undecided lanes to the tail of
+        // the queue (entry word 3 = the next call); they are picked up by the last, partly filled batch, which finishes its entries
+        // completely.  Which call decides a lane does not depend on who executes it: same results as mc_finish per entry.
+        int total = min(k.n_queued, q.cap);
+        for (int base = 0; base < total; base += 32) {
+            const int e = base + lane;
+            const bool last = total <= base + 32;  // warp-uniform: nothing appended now would be reached by a later batch
+            uint32_t eq = 0u, sel = 0u, off = 0u, word_id = 0u;
+            int j = 2;
+            if (e < total) {
+                const uint4 ent = g.my_q[e];
+                off = ent.x;
+                eq = ent.y;
+                sel = ent.z;
+                j = 2 + (int)ent.w;
+                const uint32_t yw = ((uint32_t)s.y_first << lw) + (off & ~(uint32_t)(W - 1));
+                word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (off & (uint32_t)(W - 1)));
+                if (last) {
+                    plane_c[off] ^= mc_finish(eq, sel, j, tab, g.head, seed, word_id, g.c3_base);
+                    eq = 0u;
+                } else {
+                    uint32_t lt = 0u;
+                    mc_compare4(mc_philox_j(g.head, seed, word_id, g.c3_base, j), tab, 4 * j, sel, eq, lt);
+                    plane_c[off] ^= lt;
+                    if (j >= 7) eq = 0u;  // call 7 was the last one (32 planes): whatever is still equal does not flip (U == T)
+                }
+            }
+            if (!last) {
+                const unsigned again = __ballot_sync(0xFFFFFFFFu, eq != 0u);
+                if (again != 0u) {  // warp-uniform
+                    if (eq != 0u) {
+                        const int slot = total + __popc(again & g.lanes_below);
+                        if (slot < q.cap) g.my_q[slot] = make_uint4(off, eq, sel, (uint32_t)(j + 1 - 2));
+                        else plane_c[off] ^= mc_finish(eq, sel, j + 1, tab, g.head, seed, word_id, g.c3_base);  // segment full (see mc_push)
+                    }
+                    total = min(total + __popc(again), q.cap);
+                    __syncwarp();
+                }
+            }
+        }
     }
     __syncthreads();
 }
@@ -434,12 +479,12 @@ __device__ __forceinline__ void mc_half_sweep(const Strip0 &s, int c, int lr_lo,
 __device__ __forceinline__ void mc_half_sweep_strip(const Strip0 &s, int c, int lr_lo, int nrows, int lw, uint32_t anti,
                                                     const McTable *tab, const McQueue &q, uint64_t seed, uint32_t replica,
                                                     unsigned long long sweep) {
-    if (s.W == 64) mc_half_sweep_t<64>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+    if (s.W == 64) mc_half_sweep_t<64, true>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
 #if !defined(MCRG_FEWER_INSTANTIATIONS)
-    else if (s.W == 256) mc_half_sweep_t<256>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
-    else if (s.W == 16) mc_half_sweep_t<16>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+    else if (s.W == 256) mc_half_sweep_t<256, true>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+    else if (s.W == 16) mc_half_sweep_t<16, true>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
 #endif
-    else mc_half_sweep_t<0>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
+    else mc_half_sweep_t<0, true>(s, c, lr_lo, nrows, lw, anti, tab, q, seed, replica, sweep);
 }
 
 // MEASURE phase of a strip whose words are full (bits == 32, L >= 64): the same counts and block words as measure_pair0
