@@ -184,6 +184,27 @@ struct McTable {
     uint32_t tm[32][2];  // [plane][0: T4 bit, 1: T8 bit] as 0 / 0xFFFFFFFF
 };
 
+// The table of the strip / resident kernels is ONE static shared variable referenced by name (mc_table()): its address is an
+// immediate of the LDS.  Reached through a generic pointer in a struct, the compiler rebuilt the shared-window address inside
+// the row loop (S2R + MOV + LEA per row pair) rather than keep it in a register.  k_resident_multi, whose lanes have different
+// tables, passes pointers (mc_compare4 below).
+__device__ __forceinline__ McTable &mc_table() {
+    __shared__ __align__(16) McTable tab;
+    return tab;
+}
+
+__device__ __forceinline__ void mc_compare4_s(const U4 &r, uint32_t tab_s, int plane0, uint32_t sel, uint32_t &eq, uint32_t &lt) {
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        uint32_t t4, t8;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t4), "=r"(t8) : "r"(tab_s + 8u * (uint32_t)(plane0 + e)));
+        const uint32_t tm = (sel & t4) | (~sel & t8);
+        lt |= eq & ~rr[e] & tm;
+        eq &= ~(rr[e] ^ tm);
+    }
+}
+
 __device__ __forceinline__ void mc_compare4(const U4 &r, const McTable *tab, int plane0, uint32_t sel, uint32_t &eq,
                                             uint32_t &lt) {
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -209,6 +230,13 @@ __device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0,
     return lt;
 }
 
+__device__ __forceinline__ uint32_t mc_finish_s(uint32_t eq, uint32_t sel, int j0, uint32_t tab_s, const McPhiloxHead &h, uint64_t seed,
+                                                uint32_t word_id, uint32_t c3_base) {
+    uint32_t lt = 0;
+    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4_s(mc_philox_j(h, seed, word_id, c3_base, j), tab_s, 4 * j, sel, eq, lt);
+    return lt;
+}
+
 // One half-sweep (colour c) over local rows [lr_lo, lr_lo + nrows).
 // Thread layout: column w = tid & (W-1), row group g = tid >> lw; a group owns a CONTIGUOUS block of rows and every
 // thread walks down its column.  The other-colour words above / at / below the current row then form a sliding window
@@ -230,7 +258,7 @@ struct McWalk {
 
 struct McConst {
     uint4 *my_q;         // this warp's queue segment: {offset, undecided lanes, selector, -}
-    const McTable *tab;
+    uint32_t tab_s;      // shared-space address of the threshold table, pinned in a register (see mc_half_sweep_t)
     McPhiloxHead head;   // the part of Philox rounds 0 and 1 that is constant over the half-sweep
     uint64_t seed;
     uint32_t replica, t_lo, c3_base, anti, mask, wid_c, yw_mask, lanes_below;
@@ -276,8 +304,8 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it, uint
         U4 r0, r1;
         mc_philox_pair(g.head, g.seed, word_id, g.c3_base, r0, r1);
         if (NZ >= 0) mc_compare4_nz<NZ>(r0, sel, eq, lt);
-        else mc_compare4(r0, g.tab, 0, sel, eq, lt);
-        mc_compare4(r1, g.tab, 4, sel, eq, lt);
+        else mc_compare4_s(r0, g.tab_s, 0, sel, eq, lt);
+        mc_compare4_s(r1, g.tab_s, 4, sel, eq, lt);
         *k.pc = t ^ (ge2 | lt);
         k.u = k.n0;
         k.n0 = d;
@@ -298,7 +326,7 @@ __device__ __forceinline__ void mc_push(McWalk &k, const McConst &g, unsigned pe
             g.my_q[slot] = make_uint4(off, eq, sel, 0u);
         } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
             const uint32_t yw = k.yw - (uint32_t)(back * g.W);
-            k.pc[-back * g.W] ^= mc_finish(eq, sel, 2, g.tab, g.head, g.seed, (yw & g.yw_mask) | g.wid_c, g.c3_base);
+            k.pc[-back * g.W] ^= mc_finish_s(eq, sel, 2, g.tab_s, g.head, g.seed, (yw & g.yw_mask) | g.wid_c, g.c3_base);
         }
     }
     k.n_queued += __popc(pend);
@@ -346,7 +374,10 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     const uint32_t *plane_o = s.base + o * s.rows * W;
     McConst g;
     g.my_q = q.ent + q.cap * warp;  // this warp's segment: q.cap entries
-    g.tab = tab;
+    {
+        const uint32_t t0 = smem_u32(&mc_table());
+        asm volatile("mov.u32 %0, %1;" : "=r"(g.tab_s) : "r"(t0));  // opaque: the compiler cannot rematerialise it inside the row loop
+    }
     g.seed = seed;
     g.replica = replica;
     g.t_lo = (uint32_t)sweep;
@@ -401,8 +432,9 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     k.n_queued = 0;
     const int par0 = (s.y_first + lr0 + c) & 1;  // warp-uniform (W >= 32: one group per warp; W < 32: chunk even)
     // thresholds below 1/4 (every coupling of the critical region): cheaper first compare, see mc_compare4_nz
-    const bool nz = (tab->tm[0][0] | tab->tm[1][0] | tab->tm[0][1] | tab->tm[1][1] | tab->tm[2][1] | tab->tm[3][1]) == 0u;
-    const int xy = (tab->tm[2][0] ? 2 : 0) | (tab->tm[3][0] ? 1 : 0);
+    const McTable &tb = mc_table();  // == *tab: every caller of the strip / resident kernels passes &mc_table()
+    const bool nz = (tb.tm[0][0] | tb.tm[1][0] | tb.tm[0][1] | tb.tm[1][1] | tb.tm[2][1] | tb.tm[3][1]) == 0u;
+    const int xy = (tb.tm[2][0] ? 2 : 0) | (tb.tm[3][0] ? 1 : 0);
     if (s.bits == 32) {
         if (WT >= 32) mc_walk_b32<WT, false>(nz, xy, par0, k, g, n_steps);        // W is a compile-time constant >= 32
         else if (WT > 0) mc_walk_b32<WT, true>(nz, xy, par0, k, g, n_steps);      // ... < 32
@@ -418,7 +450,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
             const uint4 ent = g.my_q[e];
             const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
             const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
-            plane_c[ent.x] ^= mc_finish(ent.y, ent.z, 2, tab, g.head, seed, word_id, g.c3_base);
+            plane_c[ent.x] ^= mc_finish_s(ent.y, ent.z, 2, g.tab_s, g.head, seed, word_id, g.c3_base);
         }
     } else {
         // Pass 2, one queue entry per lane.  A batch of 32 entries would run as many Philox calls as its unluckiest entry (after
@@ -441,11 +473,11 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
                 const uint32_t yw = ((uint32_t)s.y_first << lw) + (off & ~(uint32_t)(W - 1));
                 word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (off & (uint32_t)(W - 1)));
                 if (last) {
-                    plane_c[off] ^= mc_finish(eq, sel, j, tab, g.head, seed, word_id, g.c3_base);
+                    plane_c[off] ^= mc_finish_s(eq, sel, j, g.tab_s, g.head, seed, word_id, g.c3_base);
                     eq = 0u;
                 } else {
                     uint32_t lt = 0u;
-                    mc_compare4(mc_philox_j(g.head, seed, word_id, g.c3_base, j), tab, 4 * j, sel, eq, lt);
+                    mc_compare4_s(mc_philox_j(g.head, seed, word_id, g.c3_base, j), g.tab_s, 4 * j, sel, eq, lt);
                     plane_c[off] ^= lt;
                     if (j >= 7) eq = 0u;  // call 7 was the last one (32 planes): whatever is still equal does not flip (U == T)
                 }
@@ -456,7 +488,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
                     if (eq != 0u) {
                         const int slot = total + __popc(again & g.lanes_below);
                         if (slot < q.cap) g.my_q[slot] = make_uint4(off, eq, sel, (uint32_t)(j + 1 - 2));
-                        else plane_c[off] ^= mc_finish(eq, sel, j + 1, tab, g.head, seed, word_id, g.c3_base);  // segment full (see mc_push)
+                        else plane_c[off] ^= mc_finish_s(eq, sel, j + 1, g.tab_s, g.head, seed, word_id, g.c3_base);  // segment full (see mc_push)
                     }
                     total = min(total + __popc(again), q.cap);
                     __syncwarp();
@@ -629,7 +661,7 @@ template <bool MEASURE>
 __global__ void __launch_bounds__(SWEEP_THREADS, MCRG_SWEEP_MIN_BLOCKS) k_sweep0(const SweepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[4];
-    __shared__ __align__(16) McTable tab;
+    McTable &tab = mc_table();
     __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.y, strip = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
@@ -1031,7 +1063,7 @@ __global__ void __launch_bounds__(SMALL ? 32 : SWEEP_THREADS, SMALL ? RESIDENT_S
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ unsigned int red[(MAX_LEVELS + 1) * 4];
     __shared__ long long S_sh[X_LEN];  // the sums of the sample + the two pseudo-entries of acc_slot_decode
-    __shared__ __align__(16) McTable tab;
+    McTable &tab = mc_table();
     __shared__ __align__(8) unsigned long long bar;
     const int r = blockIdx.x;
     const int L = a.L, W = a.W, lw = ilog2(W);
