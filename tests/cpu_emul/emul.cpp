@@ -341,4 +341,81 @@ int emul_fast_paths(int n_trials, uint64_t seed0) {
     return bad;
 }
 
+// ---- pass 2 of a half-sweep as k_sweep0 schedules it (mc_half_sweep_t<.., REQUEUE = true>) -----------------------------------
+// A warp's queue of words with undecided lanes is consumed one entry per lane, 32 at a time.  Every batch but the last runs ONE
+// further Philox call per entry and appends the entries that still have undecided lanes to the tail (with the next call index);
+// the last batch finishes its entries completely; entries that do not fit the segment any more are finished on the spot.  Here:
+// the same schedule, lane by lane, against "finish every entry on its own" — the flip mask of every entry must be the same
+// whatever the queue length, the capacity and the luck of the draws.  Returns the number of entries that differ.
+int emul_requeue_pass2(int n_trials, uint64_t seed0) {
+    uint64_t x = seed0;
+    int bad = 0;
+    for (int it = 0; it < n_trials; ++it) {
+        const uint64_t seed = splitmix(x), t = splitmix(x);
+        const uint32_t replica = (uint32_t)splitmix(x);
+        const uint32_t c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((t >> 32) & 0xFFFFFu);
+        const McPhiloxHead h = mc_philox_head(seed, replica, (uint32_t)t);
+        // thresholds that leave many lanes undecided for several calls: long runs of equal leading bits are what re-queues
+        const uint32_t T4 = (it & 1) ? (uint32_t)splitmix(x) : ((uint32_t)splitmix(x) & 0x000FFFFFu), T8 = (it & 2) ? (uint32_t)splitmix(x) : 0u;
+        const int n0 = (int)(splitmix(x) % 200), cap = 8 + (int)(splitmix(x) % 220);
+        struct Ent { uint32_t word, eq, sel, j; };
+        std::vector<Ent> q;
+        std::vector<uint32_t> want, got;
+        for (int e = 0; e < n0; ++e) {
+            Ent en;
+            en.word = (uint32_t)splitmix(x) & 0x3FFFFFFu;
+            en.sel = (uint32_t)splitmix(x);
+            en.eq = (it & 4) ? (uint32_t)splitmix(x) : ((uint32_t)splitmix(x) & (uint32_t)splitmix(x) & (uint32_t)splitmix(x));
+            if (en.eq == 0u) en.eq = 1u << (e & 31);
+            en.j = 2;
+            q.push_back(en);
+        }
+        // reference: every entry finished on its own (mc_finish); entries beyond the capacity never reach the queue (mc_push
+        // finishes them inline in pass 1), so the schedule below only sees min(n0, cap)
+        const int total0 = n0 < cap ? n0 : cap;
+        auto finish = [&](uint32_t word, uint32_t eq, uint32_t sel, int j0) {
+            uint32_t lt = 0u;
+            for (int j = j0; j < 8 && eq != 0u; ++j) cmp4_generic(mc_philox_j(h, seed, word, c3_base, j), T4, T8, 4 * j, sel, eq, lt);
+            return lt;
+        };
+        // an entry keeps its word through the re-queues: make the words unique and key the result by them
+        for (int e = 0; e < total0; ++e) q[e].word = (q[e].word & 0x03FFFF00u) | (uint32_t)(e & 0xFF) | ((uint32_t)(e >> 8) << 26);
+        for (int e = 0; e < total0; ++e) want.push_back(finish(q[e].word, q[e].eq, q[e].sel, 2));
+        got.assign(total0, 0u);
+        auto index_of = [&](uint32_t word) { return (int)((word & 0xFFu) | ((word >> 26) << 8)); };
+        q.resize(cap > total0 ? cap : total0);
+        int total = total0;
+        for (int base = 0; base < total; base += 32) {
+            const bool last = total <= base + 32;
+            std::vector<Ent> again;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int e = base + lane;
+                if (e >= total) continue;
+                Ent en = q[e];
+                if (last) {
+                    got[index_of(en.word)] ^= finish(en.word, en.eq, en.sel, (int)en.j);
+                } else {
+                    uint32_t lt = 0u;
+                    cmp4_generic(mc_philox_j(h, seed, en.word, c3_base, (int)en.j), T4, T8, 4 * (int)en.j, en.sel, en.eq, lt);
+                    got[index_of(en.word)] ^= lt;
+                    if (en.j >= 7) en.eq = 0u;
+                    if (en.eq != 0u) {
+                        en.j += 1;
+                        again.push_back(en);
+                    }
+                }
+            }
+            for (size_t r = 0; r < again.size(); ++r) {  // rank among the lanes that go again
+                const int slot = total + (int)r;
+                if (slot < cap) q[slot] = again[r];
+                else got[index_of(again[r].word)] ^= finish(again[r].word, again[r].eq, again[r].sel, (int)again[r].j);
+            }
+            total = total + (int)again.size() < cap ? total + (int)again.size() : cap;  // total0 <= cap
+        }
+        for (int e = 0; e < total0; ++e)
+            if (got[e] != want[e]) ++bad;
+    }
+    return bad;
+}
+
 }  // extern "C"

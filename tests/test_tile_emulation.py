@@ -34,6 +34,8 @@ def emul():
     e.emul_hot_start.argtypes = [C.c_int, C.c_uint64, C.c_uint32, _libs.i32p]
     e.emul_fast_paths.argtypes = [C.c_int, C.c_uint64]
     e.emul_fast_paths.restype = C.c_int
+    e.emul_requeue_pass2.argtypes = [C.c_int, C.c_uint64]
+    e.emul_requeue_pass2.restype = C.c_int
     return e
 
 
@@ -137,3 +139,11 @@ def test_fast_paths_equal_the_specification(emul):
     threshold bits — against philox4x32_10 / metropolis_flip_mask of bitops.cuh (which tests above tie to the oracle):
     300 000 random words, keys, sweep counters (incl. the 32-bit boundary) and thresholds of every pattern, no disagreement."""
     assert emul.emul_fast_paths(300000, 2026) == 0
+
+
+def test_requeue_schedule_of_pass_two(emul):
+    """Pass 2 of a strip half-sweep (kernels.cu: mc_half_sweep_t<.., REQUEUE>): every batch of queued words but the last runs one
+    Philox call and re-queues what is still undecided, the last batch finishes completely, a full segment finishes on the spot —
+    the same flips per word as finishing every entry on its own, for queue lengths 0 .. 199, capacities 8 .. 227 and thresholds
+    that keep lanes undecided over several calls (2 000 random queues)."""
+    assert emul.emul_requeue_pass2(2000, 77) == 0
