@@ -2,6 +2,7 @@
 form of mcrg_run that bench.py times.  Usage (on the B200):
     compute-sanitizer --tool memcheck  python profiles/sanitize.py all
     compute-sanitizer --tool racecheck python profiles/sanitize.py sweep
+    compute-sanitizer --tool racecheck python profiles/sanitize.py requeue      # only the strips tall enough for pass 2 to re-queue
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,6 +30,11 @@ if which in ("all", "sweep"):
     print("resident L=256 (TMA)", run(256, 1))
     print("tiny L=4", run(4, 5))
     print("tiny L=8 (C1)", run(8, 9, samples=3))
+if which in ("all", "sweep", "requeue"):
+    # strips of 96 rows: a warp walks 24 rows of 32 words per half-sweep and queues ~80 words, i.e. pass 2 runs two one-call
+    # batches that re-queue and a last batch that picks the re-queued words up (mc_half_sweep_t<.., REQUEUE = true>)
+    print("strip L=4096 R=96, pass 2 with re-queueing", run(4096, 1, strip=96, samples=2))
+    print("strip L=1024 R=256 (W=16: 16 row groups), pass 2 with re-queueing", run(1024, 2, strip=256, samples=2))
 if which in ("all", "cluster"):
     print("cluster L=128", run(128, 2, cluster=True))
     print("cluster L=16", run(16, 3, cluster=True))
