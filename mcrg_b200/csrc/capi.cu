@@ -50,7 +50,7 @@ struct GraphKey {
 
 // Samples in flight: sample s measures into slot s % n_slots (its own set of blocked lattices and popcount cells) and its
 // pyramid runs on that slot's side stream, so up to n_slots pyramids overlap each other and the sweeps that follow.  The slot
-// count is chosen per context (choose_slots): as many as the largest graph holds samples when the blocked lattices are small
+// count is chosen per context (mcrg_ctx_create): as many as the largest graph holds samples when the blocked lattices are small
 // enough, so that inside a graph no measuring sweep ever waits for a pyramid to free its slot.
 #ifndef MCRG_PYR_SLOTS
 #define MCRG_PYR_SLOTS 64
