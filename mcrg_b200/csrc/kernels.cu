@@ -231,9 +231,9 @@ __device__ __forceinline__ uint32_t mc_finish(uint32_t eq, uint32_t sel, int j0,
 }
 
 __device__ __forceinline__ uint32_t mc_finish_s(uint32_t eq, uint32_t sel, int j0, uint32_t tab_s, const McPhiloxHead &h, uint64_t seed,
-                                                uint32_t word_id, uint32_t c3_base) {
+                                                uint32_t word_id, uint32_t ck) {
     uint32_t lt = 0;
-    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4_s(mc_philox_j(h, seed, word_id, c3_base, j), tab_s, 4 * j, sel, eq, lt);
+    for (int j = j0; j < 8 && eq != 0u; ++j) mc_compare4_s(mc_philox_j_ck(h, seed, word_id, ck, j), tab_s, 4 * j, sel, eq, lt);
     return lt;
 }
 
@@ -261,7 +261,7 @@ struct McConst {
     uint32_t tab_s;      // shared-space address of the threshold table, pinned in a register (see mc_half_sweep_t)
     McPhiloxHead head;   // the part of Philox rounds 0 and 1 that is constant over the half-sweep
     uint64_t seed;
-    uint32_t replica, t_lo, c3_base, anti, mask, wid_c, yw_mask, lanes_below;
+    uint32_t replica, t_lo, ck, anti, mask, wid_c, yw_mask, lanes_below;  // ck = c3_base ^ key word 1 (mc_philox_pair_ck)
     int W, bits, d_up, d_dn, qcap, n_act;
     bool w_first, w_last;  // this thread's column is the first / last word of a row
 };
@@ -302,7 +302,7 @@ __device__ __forceinline__ void mc_row(McWalk &k, const McConst &g, int it, uint
         uint32_t lt = 0;                    // subset of the initial eq, hence disjoint from the A >= 2 lanes
         const uint32_t word_id = mc_word_id(k, g);
         U4 r0, r1;
-        mc_philox_pair(g.head, g.seed, word_id, g.c3_base, r0, r1);
+        mc_philox_pair_ck(g.head, g.seed, word_id, g.ck, r0, r1);
         if (NZ >= 0) mc_compare4_nz<NZ>(r0, sel, eq, lt);
         else mc_compare4_s(r0, g.tab_s, 0, sel, eq, lt);
         mc_compare4_s(r1, g.tab_s, 4, sel, eq, lt);
@@ -326,7 +326,7 @@ __device__ __forceinline__ void mc_push(McWalk &k, const McConst &g, unsigned pe
             g.my_q[slot] = make_uint4(off, eq, sel, 0u);
         } else {  // segment full (does not happen for equilibrium-like data; kept for exactness): finish inline
             const uint32_t yw = k.yw - (uint32_t)(back * g.W);
-            k.pc[-back * g.W] ^= mc_finish_s(eq, sel, 2, g.tab_s, g.head, g.seed, (yw & g.yw_mask) | g.wid_c, g.c3_base);
+            k.pc[-back * g.W] ^= mc_finish_s(eq, sel, 2, g.tab_s, g.head, g.seed, (yw & g.yw_mask) | g.wid_c, g.ck);
         }
     }
     k.n_queued += __popc(pend);
@@ -381,11 +381,11 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
     g.seed = seed;
     g.replica = replica;
     g.t_lo = (uint32_t)sweep;
-    g.c3_base = ((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu);
+    g.ck = (((uint32_t)PURPOSE_MC << 28) | (uint32_t)((sweep >> 32) & 0xFFFFFu)) ^ (uint32_t)(seed >> 32);
     g.head = mc_philox_head(seed, replica, g.t_lo);
     g.anti = anti;
     g.mask = s.mask;
-    g.lanes_below = (1u << lane) - 1u;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(g.lanes_below));  // one S2R if the compiler rematerialises it (it did: S2R tid + MOV + SHF)
     g.W = W;
     g.bits = s.bits;
     g.qcap = q.cap;
@@ -450,7 +450,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
             const uint4 ent = g.my_q[e];
             const uint32_t yw = ((uint32_t)s.y_first << lw) + (ent.x & ~(uint32_t)(W - 1));
             const uint32_t word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (ent.x & (uint32_t)(W - 1)));
-            plane_c[ent.x] ^= mc_finish_s(ent.y, ent.z, 2, g.tab_s, g.head, seed, word_id, g.c3_base);
+            plane_c[ent.x] ^= mc_finish_s(ent.y, ent.z, 2, g.tab_s, g.head, seed, word_id, g.ck);
         }
     } else {
         // Pass 2, one queue entry per lane.  A batch of 32 entries would run as many Philox calls as its unluckiest entry (after
@@ -473,11 +473,11 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
                 const uint32_t yw = ((uint32_t)s.y_first << lw) + (off & ~(uint32_t)(W - 1));
                 word_id = (yw & g.yw_mask) | ((uint32_t)(c * s.L * W) + (off & (uint32_t)(W - 1)));
                 if (last) {
-                    plane_c[off] ^= mc_finish_s(eq, sel, j, g.tab_s, g.head, seed, word_id, g.c3_base);
+                    plane_c[off] ^= mc_finish_s(eq, sel, j, g.tab_s, g.head, seed, word_id, g.ck);
                     eq = 0u;
                 } else {
                     uint32_t lt = 0u;
-                    mc_compare4_s(mc_philox_j(g.head, seed, word_id, g.c3_base, j), g.tab_s, 4 * j, sel, eq, lt);
+                    mc_compare4_s(mc_philox_j_ck(g.head, seed, word_id, g.ck, j), g.tab_s, 4 * j, sel, eq, lt);
                     plane_c[off] ^= lt;
                     if (j >= 7) eq = 0u;  // call 7 was the last one (32 planes): whatever is still equal does not flip (U == T)
                 }
@@ -488,7 +488,7 @@ __device__ __forceinline__ void mc_half_sweep_t(const Strip0 &s, int c, int lr_l
                     if (eq != 0u) {
                         const int slot = total + __popc(again & g.lanes_below);
                         if (slot < q.cap) g.my_q[slot] = make_uint4(off, eq, sel, (uint32_t)(j + 1 - 2));
-                        else plane_c[off] ^= mc_finish_s(eq, sel, j + 1, g.tab_s, g.head, seed, word_id, g.c3_base);  // segment full (see mc_push)
+                        else plane_c[off] ^= mc_finish_s(eq, sel, j + 1, g.tab_s, g.head, seed, word_id, g.ck);  // segment full (see mc_push)
                     }
                     total = min(total + __popc(again), q.cap);
                     __syncwarp();

@@ -108,6 +108,31 @@ MCRG_HD void mc_philox_pair(const McPhiloxHead &h, uint64_t seed, uint32_t word_
     r1 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
 }
 
+// The same two functions with c3_base ^ k1 formed once per half-sweep (`ck`; the call index occupies bits of c3_base that are zero,
+// so OR-ing it in equals XOR-ing it in): the row loop then has no use for the key word k1 any more — it had been re-read from
+// the constant bank every row pair.
+MCRG_HD void mc_philox_pair_ck(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t ck, U4 &r0, U4 &r1) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t ph, pl;
+    mulwide(0xD2511F53u, word_id, ph, pl);
+    const uint32_t c2a = ph ^ ck;
+    const uint32_t c2b = c2a ^ (1u << 20);
+    const uint32_t c2n = h.h1 ^ pl ^ (k1 + 0xBB67AE85u);
+    uint32_t qh, ql;
+    mulwide(0xCD9E8D57u, c2a, qh, ql);
+    r0 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
+    mulwide(0xCD9E8D57u, c2b, qh, ql);
+    r1 = mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, c2n, h.l1, k0, k1);
+}
+
+MCRG_HD U4 mc_philox_j_ck(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t ck, int j) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t ph, pl, qh, ql;
+    mulwide(0xD2511F53u, word_id, ph, pl);
+    mulwide(0xCD9E8D57u, ph ^ ck ^ ((uint32_t)j << 20), qh, ql);
+    return mc_philox_rounds2to9(qh ^ h.b0 ^ (k0 + 0x9E3779B9u), ql, h.h1 ^ pl ^ (k1 + 0xBB67AE85u), h.l1, k0, k1);
+}
+
 // call j of word `word_id` with the shared head (pass 2 and the inline overflow path)
 MCRG_HD U4 mc_philox_j(const McPhiloxHead &h, uint64_t seed, uint32_t word_id, uint32_t c3_base, int j) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);

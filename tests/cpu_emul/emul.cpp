@@ -296,6 +296,13 @@ int emul_fast_paths(int n_trials, uint64_t seed0) {
         if (!same(r1, philox_keyed(seed, word, replica, t, PURPOSE_MC, 1))) ++bad;
         for (int j = 0; j < 8; ++j)
             if (!same(mc_philox_j(h, seed, word, c3_base, j), philox_keyed(seed, word, replica, t, PURPOSE_MC, j))) ++bad;
+        // the forms the strip / resident kernels call: c3_base ^ key word 1 formed once (mc_philox_pair_ck, mc_philox_j_ck)
+        const uint32_t ck = c3_base ^ (uint32_t)(seed >> 32);
+        U4 s0, s1;
+        mc_philox_pair_ck(h, seed, word, ck, s0, s1);
+        if (!same(s0, r0) || !same(s1, r1)) ++bad;
+        for (int j = 0; j < 8; ++j)
+            if (!same(mc_philox_j_ck(h, seed, word, ck, j), philox_keyed(seed, word, replica, t, PURPOSE_MC, j))) ++bad;
         // (2) one word update: thresholds of every leading-bit pattern (and general ones), spins near and far from order
         McParams p;
         p.seed = seed;
